@@ -1,0 +1,40 @@
+/* prostt5_b200_debug.h — kernel-level test entry points of libprostt5_b200.so.
+ *
+ * These are NOT part of the drop-in boundary (that is prostt5_b200.h).  They let tests/ drive each
+ * sm_100a kernel of the hot path in isolation through the C ABI, host buffers in and out, and let
+ * bench.py time the dominant kernel on its own stream.  Every function returns 0 on success and a
+ * P5_ERR_* code otherwise; the message is available from p5_last_error().
+ *
+ * There is no reference interface behind these: the reference (steineggerlab/unicore) reaches the
+ * arithmetic only through `foldseek createdb --prostt5-model` [REF src/modules/createdb.rs:158-166].
+ */
+#ifndef PROSTT5_B200_DEBUG_H
+#define PROSTT5_B200_DEBUG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* tcgen05 GEMM  C[M,N] (op)= A[M,K] * B[N,K]^T,  A and B fp16 row-major (K contiguous).
+ * variant : 0 = one CTA per 128x256 tile, 1 = CTA pair (cta_group::2) per 256x256 tile
+ * epilogue: 0 = C fp16 = acc; 1 = C fp16 = relu(acc); 2 = C fp32 += acc; 3 = C fp32 = acc
+ * c_host  : in/out, M*N elements of the epilogue's type (read for epilogue 2)
+ * iters>0 : additionally time `iters` back-to-back launches (CUDA events on the launch stream) and
+ *           store the mean milliseconds per launch in *ms_out.  c_host always holds the FIRST result. */
+int p5_dbg_gemm(int device, int variant, int epilogue, uint32_t M, uint32_t N, uint32_t K, const uint16_t* a_host,
+                const uint16_t* b_host, void* c_host, int iters, float* ms_out);
+
+/* Timing only: same GEMM on device-generated pseudo-random operands (no host copies); mean ms per
+ * launch over `iters` back-to-back launches after 3 warm-up launches. */
+int p5_dbg_gemm_bench(int device, int variant, int epilogue, uint32_t M, uint32_t N, uint32_t K, int iters,
+                      float* ms_out);
+
+/* Thread-local message of the last failed call on this thread (also declared in prostt5_b200.h). */
+const char* p5_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

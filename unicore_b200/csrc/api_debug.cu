@@ -1,0 +1,129 @@
+// Kernel-level test entry points of the C ABI (include/prostt5_b200_debug.h).  They exist so the
+// parity tests can drive each sm_100a kernel in isolation, through the same shared library and the
+// same launchers the product path uses, with host buffers in and out.
+#include <cuda_fp16.h>
+
+#include <vector>
+
+#include "common.h"
+#include "gemm.cuh"
+#include "gemm_launch.h"
+#include "prostt5_b200_debug.h"
+
+namespace p5 {
+
+namespace {
+thread_local std::string g_last_error;
+}
+
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const char* last_error_cstr() { return g_last_error.c_str(); }
+
+struct DevBuf {
+    void* p = nullptr;
+    explicit DevBuf(size_t bytes) { P5_CUDA(cudaMalloc(&p, bytes ? bytes : 1)); }
+    ~DevBuf() { cudaFree(p); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+}  // namespace p5
+
+using namespace p5;
+
+extern "C" int p5_dbg_gemm(int device, int variant, int epilogue, uint32_t M, uint32_t N, uint32_t K,
+                           const uint16_t* a_host, const uint16_t* b_host, void* c_host, int iters, float* ms_out) {
+    return guarded([&] {
+        P5_REQUIRE(a_host && b_host && c_host, P5_ERR_ARG, "null buffer");
+        P5_REQUIRE(epilogue >= 0 && epilogue <= 3, P5_ERR_ARG, "bad epilogue %d", epilogue);
+        P5_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        P5_CUDA(cudaGetDeviceProperties(&prop, device));
+        P5_REQUIRE(prop.major == 10, P5_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is sm_100a only", device,
+                   prop.major, prop.minor);
+        const Epi epi = static_cast<Epi>(epilogue);
+        const bool f16_out = (epi == Epi::StoreF16 || epi == Epi::StoreF16Relu);
+        const size_t c_bytes = size_t(M) * N * (f16_out ? 2 : 4);
+        DevBuf a(size_t(M) * K * 2), b(size_t(N) * K * 2), c(c_bytes);
+        P5_CUDA(cudaMemcpy(a.p, a_host, size_t(M) * K * 2, cudaMemcpyHostToDevice));
+        P5_CUDA(cudaMemcpy(b.p, b_host, size_t(N) * K * 2, cudaMemcpyHostToDevice));
+        P5_CUDA(cudaMemcpy(c.p, c_host, c_bytes, cudaMemcpyHostToDevice));
+        cudaStream_t st;
+        P5_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        gemm_fp16(st, prop.multiProcessorCount, variant, epi, a.p, K, b.p, K, c.p, N, M, N, K);
+        P5_CUDA(cudaStreamSynchronize(st));
+        P5_CUDA(cudaMemcpy(c_host, c.p, c_bytes, cudaMemcpyDeviceToHost));
+        if (iters > 0 && ms_out) {
+            // timing runs re-apply the epilogue to the device copy only; c_host holds the first result
+            cudaEvent_t e0, e1;
+            P5_CUDA(cudaEventCreate(&e0));
+            P5_CUDA(cudaEventCreate(&e1));
+            CUtensorMap ta = make_kmajor_tensor_map(a.p, M, K, K, kGemmBlockM);
+            CUtensorMap tb = make_kmajor_tensor_map(b.p, N, K, K, gemm_b_box_rows(variant));
+            for (int i = 0; i < 3; ++i) gemm_launch(st, prop.multiProcessorCount, variant, epi, ta, tb, c.p, N, M, N, K);
+            P5_CUDA(cudaEventRecord(e0, st));
+            for (int i = 0; i < iters; ++i)
+                gemm_launch(st, prop.multiProcessorCount, variant, epi, ta, tb, c.p, N, M, N, K);
+            P5_CUDA(cudaEventRecord(e1, st));
+            P5_CUDA(cudaStreamSynchronize(st));
+            float ms = 0.f;
+            P5_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            *ms_out = ms / iters;
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
+        cudaStreamDestroy(st);
+    });
+}
+
+namespace p5 {
+// pseudo-random fp16 in [-1,1): realistic bit toggling for timing runs (power draw depends on data)
+__global__ void fill_random_f16(__half* p, size_t n, uint32_t seed) {
+    size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    for (; i < n; i += stride) {
+        uint32_t x = static_cast<uint32_t>(i) * 2654435761u ^ seed;
+        x ^= x >> 15; x *= 2246822519u; x ^= x >> 13; x *= 3266489917u; x ^= x >> 16;
+        p[i] = __float2half(static_cast<float>(x & 0xFFFF) * (1.0f / 32768.0f) - 1.0f);
+    }
+}
+}  // namespace p5
+
+extern "C" int p5_dbg_gemm_bench(int device, int variant, int epilogue, uint32_t M, uint32_t N, uint32_t K, int iters,
+                                 float* ms_out) {
+    return guarded([&] {
+        P5_REQUIRE(epilogue >= 0 && epilogue <= 3 && iters > 0 && ms_out, P5_ERR_ARG, "bad argument");
+        P5_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        P5_CUDA(cudaGetDeviceProperties(&prop, device));
+        P5_REQUIRE(prop.major == 10, P5_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is sm_100a only", device,
+                   prop.major, prop.minor);
+        const Epi epi = static_cast<Epi>(epilogue);
+        const bool f16_out = (epi == Epi::StoreF16 || epi == Epi::StoreF16Relu);
+        const size_t c_bytes = size_t(M) * N * (f16_out ? 2 : 4);
+        DevBuf a(size_t(M) * K * 2), b(size_t(N) * K * 2), c(c_bytes);
+        cudaStream_t st;
+        P5_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        fill_random_f16<<<1184, 256, 0, st>>>(static_cast<__half*>(a.p), size_t(M) * K, 1u);
+        fill_random_f16<<<1184, 256, 0, st>>>(static_cast<__half*>(b.p), size_t(N) * K, 2u);
+        P5_CUDA(cudaMemsetAsync(c.p, 0, c_bytes, st));
+        cudaEvent_t e0, e1;
+        P5_CUDA(cudaEventCreate(&e0));
+        P5_CUDA(cudaEventCreate(&e1));
+        CUtensorMap ta = make_kmajor_tensor_map(a.p, M, K, K, kGemmBlockM);
+        CUtensorMap tb = make_kmajor_tensor_map(b.p, N, K, K, gemm_b_box_rows(variant));
+        for (int i = 0; i < 3; ++i) gemm_launch(st, prop.multiProcessorCount, variant, epi, ta, tb, c.p, N, M, N, K);
+        P5_CUDA(cudaEventRecord(e0, st));
+        for (int i = 0; i < iters; ++i) gemm_launch(st, prop.multiProcessorCount, variant, epi, ta, tb, c.p, N, M, N, K);
+        P5_CUDA(cudaEventRecord(e1, st));
+        P5_CUDA(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        P5_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        *ms_out = ms / iters;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaStreamDestroy(st);
+    });
+}
+
+extern "C" const char* p5_last_error(void) { return p5::last_error_cstr(); }

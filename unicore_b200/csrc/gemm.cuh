@@ -1,0 +1,250 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] (op)= A[M,K] * B[N,K]^T
+// A = activations (fp16, K contiguous), B = weights as stored in the gguf ([out,in], K contiguous),
+// fp32 accumulation in TMEM.  This single template is the QKV / O / FFN-in / FFN-out / conv-head
+// projection of the ProstT5 encoder (SURVEY.md §2.4 K3,K5,K6,K7,K9; arithmetic spec §8a p4,p7,p8,p10).
+//
+// Roles (256 threads, 1 CTA per SM):
+//   warp 0   TMA producer   (one elected lane) : global -> 128B-swizzled smem ring, kStages deep
+//   warp 1   MMA issuer     (one lane, leader CTA only in pair mode) : tcgen05.mma, commits to mbarriers
+//   warp 2   TMEM allocator (2 accumulator stages x kBlockN columns)
+//   warp 3   idle
+//   warps 4-7 epilogue      : tcgen05.ld -> registers -> fused op -> global (overlaps next tile's MMAs)
+// kCtaGroup == 2 pairs two SMs on one 256 x kBlockN tile (cta_group::2): each CTA loads its own 128
+// rows of A and HALF of the B tile, halving B traffic per SM.
+#pragma once
+#include "ptx.cuh"
+
+namespace p5 {
+
+enum class Epi : int {
+    StoreF16 = 0,      // C = fp16(acc)
+    StoreF16Relu = 1,  // C = fp16(max(acc,0))            (FFN-in, p8)
+    AddF32 = 2,        // C(fp32) += acc                  (residual add of O / FFN-out, p7/p8)
+    StoreF32 = 3,      // C(fp32) = acc                   (conv-head taps, p10)
+};
+
+struct GemmShape {
+    uint32_t M, N, K;
+    uint32_t ldc;  // elements
+};
+
+constexpr uint32_t kGemmBlockM = 128;  // rows per CTA (= TMEM lanes)
+constexpr uint32_t kGemmBlockK = 64;   // 64 fp16 = one 128-byte swizzle atom
+constexpr uint32_t kUmmaK = 16;
+constexpr uint32_t kGemmThreads = 256;
+constexpr uint32_t kBandM = 8;  // m-tiles per L2 band of the tile order
+
+template <int kCtaGroup, int kBlockN, int kStages>
+struct GemmSmem {
+    static constexpr uint32_t kLoadN = kBlockN / kCtaGroup;
+    static constexpr uint32_t kABytes = kGemmBlockM * kGemmBlockK * 2;
+    static constexpr uint32_t kBBytes = kLoadN * kGemmBlockK * 2;
+    static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+    static constexpr uint32_t kBarOffset = kStages * kStageBytes;
+    // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem ptr
+    static constexpr uint32_t kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16;
+    static constexpr uint32_t kDynamic = kTotal + 1024;  // slack for manual 1024 B alignment
+};
+
+__device__ __forceinline__ void tile_coords(uint32_t t, uint32_t num_mt, uint32_t num_nt, uint32_t& mt,
+                                            uint32_t& nt) {
+    const uint32_t band_tiles = kBandM * num_nt;
+    const uint32_t band = t / band_tiles;
+    const uint32_t r = t - band * band_tiles;
+    const uint32_t m_first = band * kBandM;
+    const uint32_t band_h = min(kBandM, num_mt - m_first);
+    nt = r / band_h;
+    mt = m_first + (r - nt * band_h);
+}
+
+template <int kCtaGroup, int kBlockN, int kStages, Epi kEpi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    void* __restrict__ Cptr, GemmShape s) {
+    using L = GemmSmem<kCtaGroup, kBlockN, kStages>;
+    constexpr uint32_t kUmmaM = kGemmBlockM * kCtaGroup;
+    constexpr uint32_t kTmemCols = 2 * kBlockN;
+    static_assert(kTmemCols == 64 || kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM columns");
+    static_assert(kBlockN % 32 == 0 && kBlockN <= 256, "tile N");
+
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B atoms need 1024-byte aligned tile bases
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kStages * L::kABytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full_bar = empty_bar + kStages;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const uint32_t warp_idx = threadIdx.x >> 5;  // warp-uniform
+    const uint32_t lane = ptx::lane_id();
+    const uint32_t cta_rank = (kCtaGroup == 2) ? ptx::cluster_ctarank() : 0u;
+    const bool is_leader = cta_rank == 0;
+
+    if (warp_idx == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tma_a);
+        ptx::prefetch_tensormap(&tma_b);
+    }
+    if (warp_idx == 1 && lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kStages; ++i) {
+            ptx::mbar_init(&full_bar[i], kCtaGroup);  // producer arrive of each CTA of the pair
+            ptx::mbar_init(&empty_bar[i], 1);         // one tcgen05.commit
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tmem_full_bar[i], 1);               // one tcgen05.commit
+            ptx::mbar_init(&tmem_empty_bar[i], 4 * kCtaGroup);  // one arrive per epilogue warp
+        }
+        ptx::fence_mbar_init();
+    }
+    if constexpr (kCtaGroup == 2) ptx::cluster_sync();
+    if (warp_idx == 2) ptx::tmem_alloc<kCtaGroup>(tmem_ptr_smem, kTmemCols);
+    ptx::tc_fence_before();
+    if constexpr (kCtaGroup == 2) ptx::cluster_sync(); else __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
+
+    const uint32_t num_mt = (s.M + kUmmaM - 1) / kUmmaM;
+    const uint32_t num_nt = (s.N + kBlockN - 1) / kBlockN;
+    const uint32_t num_tiles = num_mt * num_nt;
+    const uint32_t num_kb = (s.K + kGemmBlockK - 1) / kGemmBlockK;
+    const uint32_t cluster_id = blockIdx.x / kCtaGroup;
+    const uint32_t num_clusters = gridDim.x / kCtaGroup;
+
+    if (warp_idx == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters) {
+                uint32_t mt, nt;
+                tile_coords(t, num_mt, num_nt, mt, nt);
+                const int32_t m_idx = static_cast<int32_t>((mt * kCtaGroup + cta_rank) * kGemmBlockM);
+                const int32_t n_idx = static_cast<int32_t>(nt * kBlockN + cta_rank * L::kLoadN);
+                for (uint32_t kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    const int32_t k_idx = static_cast<int32_t>(kb * kGemmBlockK);
+                    uint8_t* sa = smem_a + stage * L::kABytes;
+                    uint8_t* sb = smem_b + stage * L::kBBytes;
+                    if constexpr (kCtaGroup == 1) {
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+                        ptx::tma_load_2d(&tma_a, &full_bar[stage], sa, k_idx, m_idx, ptx::kEvictNormal);
+                        ptx::tma_load_2d(&tma_b, &full_bar[stage], sb, k_idx, n_idx, ptx::kEvictLast);
+                    } else {
+                        if (is_leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes * 2);
+                        ptx::tma_load_2d_pair(&tma_a, &full_bar[stage], sa, k_idx, m_idx, ptx::kEvictNormal);
+                        ptx::tma_load_2d_pair(&tma_b, &full_bar[stage], sb, k_idx, n_idx, ptx::kEvictLast);
+                        if (!is_leader) ptx::mbar_arrive_cluster(&full_bar[stage], 0);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================== MMA issuer =====================
+        if (is_leader) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16_f32(kUmmaM, kBlockN);
+            uint32_t stage = 0, phase = 0, accum_iter = 0;
+            for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++accum_iter) {
+                const uint32_t as = accum_iter & 1u;
+                const uint32_t aphase = (accum_iter >> 1) & 1u;
+                ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * kBlockN;
+                for (uint32_t kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    if (lane == 0) {
+                        const uint64_t a_desc = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem_a + stage * L::kABytes));
+                        const uint64_t b_desc = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem_b + stage * L::kBBytes));
+#pragma unroll
+                        for (uint32_t k = 0; k < kGemmBlockK / kUmmaK; ++k) {
+                            // +32 bytes per UMMA_K step inside the 128-byte swizzle atom
+                            const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+                            ptx::umma_f16<kCtaGroup>(tmem_d, a_desc + koff, b_desc + koff, idesc, (kb | k) != 0u);
+                        }
+                        ptx::umma_commit<kCtaGroup>(&empty_bar[stage]);  // smem slot free when MMAs retire
+                        if (kb == num_kb - 1) ptx::umma_commit<kCtaGroup>(&tmem_full_bar[as]);
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp_idx >= 4) {
+        // ===================== epilogue =====================
+        const uint32_t ew = warp_idx - 4;  // == warp_idx % 4: the TMEM lane quarter this warp may read
+        uint32_t accum_iter = 0;
+        for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++accum_iter) {
+            uint32_t mt, nt;
+            tile_coords(t, num_mt, num_nt, mt, nt);
+            const uint32_t as = accum_iter & 1u;
+            const uint32_t aphase = (accum_iter >> 1) & 1u;
+            const uint32_t row = (mt * kCtaGroup + cta_rank) * kGemmBlockM + ew * 32 + lane;
+            const uint32_t n_base = nt * kBlockN;
+            ptx::mbar_wait(&tmem_full_bar[as], aphase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((ew * 32u) << 16) + as * kBlockN;
+#pragma unroll 1
+            for (uint32_t c = 0; c < kBlockN / 32; ++c) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+                ptx::tmem_ld_wait();
+                const uint32_t col0 = n_base + c * 32;
+                if (row < s.M && col0 < s.N) {
+                    const uint32_t ncols = min(32u, s.N - col0);  // multiple of 8 (checked on host)
+                    if constexpr (kEpi == Epi::StoreF16 || kEpi == Epi::StoreF16Relu) {
+                        __half* crow = reinterpret_cast<__half*>(Cptr) + static_cast<size_t>(row) * s.ldc + col0;
+#pragma unroll
+                        for (uint32_t j = 0; j < 4; ++j) {
+                            if (j * 8 < ncols) {
+                                uint32_t pk[4];
+#pragma unroll
+                                for (uint32_t q = 0; q < 4; ++q) {
+                                    float x0 = __uint_as_float(v[j * 8 + 2 * q]);
+                                    float x1 = __uint_as_float(v[j * 8 + 2 * q + 1]);
+                                    if constexpr (kEpi == Epi::StoreF16Relu) {
+                                        x0 = fmaxf(x0, 0.f);
+                                        x1 = fmaxf(x1, 0.f);
+                                    }
+                                    __half2 h = __floats2half2_rn(x0, x1);
+                                    pk[q] = *reinterpret_cast<uint32_t*>(&h);
+                                }
+                                *reinterpret_cast<uint4*>(crow + j * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                        }
+                    } else {
+                        float* crow = reinterpret_cast<float*>(Cptr) + static_cast<size_t>(row) * s.ldc + col0;
+#pragma unroll
+                        for (uint32_t j = 0; j < 8; ++j) {
+                            if (j * 4 < ncols) {
+                                float4 x = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                                if constexpr (kEpi == Epi::AddF32) {
+                                    const float4 o = *reinterpret_cast<const float4*>(crow + j * 4);
+                                    x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
+                                }
+                                *reinterpret_cast<float4*>(crow + j * 4) = x;
+                            }
+                        }
+                    }
+                }
+            }
+            // accumulator stage drained: hand it back to the MMA issuer of the leader CTA
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (kCtaGroup == 1) ptx::mbar_arrive(&tmem_empty_bar[as]);
+                else ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    if constexpr (kCtaGroup == 2) ptx::cluster_sync(); else __syncthreads();
+    if (warp_idx == 2) ptx::tmem_dealloc<kCtaGroup>(tmem_base, kTmemCols);
+}
+
+}  // namespace p5

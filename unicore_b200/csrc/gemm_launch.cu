@@ -1,0 +1,131 @@
+// Host-side launcher for the tcgen05 GEMM: tensor-map encoding (driver entry point resolved at run
+// time, so the library links against cudart only) and template dispatch.
+#include "gemm_launch.h"
+
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.h"
+#include "gemm.cuh"
+
+namespace p5 {
+
+namespace {
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    P5_REQUIRE(fn != nullptr, P5_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    return fn;
+}
+
+}  // namespace
+
+// rows x cols fp16 matrix, cols contiguous, row pitch `ld` elements; box = box_rows x 64 columns,
+// 128-byte swizzle (matches make_kmajor_sw128_desc).  Out-of-bounds elements read as zero.
+CUtensorMap make_kmajor_tensor_map(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    P5_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, P5_ERR_ARG, "GEMM operand is not 16-byte aligned");
+    P5_REQUIRE((ld * 2) % 16 == 0, P5_ERR_ARG, "GEMM operand row pitch (%llu elements) is not a multiple of 8",
+               (unsigned long long)ld);
+    P5_REQUIRE(box_rows >= 1 && box_rows <= 256, P5_ERR_ARG, "bad TMA box");
+    CUtensorMap m;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * 2};
+    cuuint32_t box[2] = {kGemmBlockK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    P5_REQUIRE(r == CUDA_SUCCESS, P5_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return m;
+}
+
+namespace {
+
+template <int kCtaGroup, int kBlockN, int kStages, Epi kEpi>
+void launch_one(cudaStream_t stream, int num_sms, const CUtensorMap& ta, const CUtensorMap& tb, void* C,
+                const GemmShape& s) {
+    using L = GemmSmem<kCtaGroup, kBlockN, kStages>;
+    auto kernel = gemm_tcgen05_kernel<kCtaGroup, kBlockN, kStages, kEpi>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] {
+        attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kDynamic);
+    });
+    P5_CUDA(attr_err);
+    const uint32_t num_mt = (s.M + kGemmBlockM * kCtaGroup - 1) / (kGemmBlockM * kCtaGroup);
+    const uint32_t num_nt = (s.N + kBlockN - 1) / kBlockN;
+    const uint32_t tiles = num_mt * num_nt;
+    uint32_t clusters = static_cast<uint32_t>(num_sms / kCtaGroup);
+    if (tiles < clusters) clusters = tiles;
+    if (clusters == 0) return;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * kCtaGroup, 1, 1);
+    cfg.blockDim = dim3(kGemmThreads, 1, 1);
+    cfg.dynamicSmemBytes = L::kDynamic;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCtaGroup;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    P5_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, C, s));
+}
+
+template <int kCtaGroup, int kBlockN, int kStages>
+void launch_epi(cudaStream_t stream, int num_sms, Epi epi, const CUtensorMap& ta, const CUtensorMap& tb, void* C,
+                const GemmShape& s) {
+    switch (epi) {
+        case Epi::StoreF16: launch_one<kCtaGroup, kBlockN, kStages, Epi::StoreF16>(stream, num_sms, ta, tb, C, s); break;
+        case Epi::StoreF16Relu: launch_one<kCtaGroup, kBlockN, kStages, Epi::StoreF16Relu>(stream, num_sms, ta, tb, C, s); break;
+        case Epi::AddF32: launch_one<kCtaGroup, kBlockN, kStages, Epi::AddF32>(stream, num_sms, ta, tb, C, s); break;
+        case Epi::StoreF32: launch_one<kCtaGroup, kBlockN, kStages, Epi::StoreF32>(stream, num_sms, ta, tb, C, s); break;
+    }
+}
+
+}  // namespace
+
+uint32_t gemm_b_box_rows(int variant) {
+    switch (variant) {
+        case 0: return 256;  // 1 CTA, full 256-row B tile
+        case 1: return 128;  // CTA pair, each CTA loads half of the 256-row B tile
+        default: throw Error(P5_ERR_ARG, strf("unknown GEMM variant %d", variant));
+    }
+}
+
+void gemm_launch(cudaStream_t stream, int num_sms, int variant, Epi epi, const CUtensorMap& tma_a,
+                 const CUtensorMap& tma_b, void* C, uint32_t ldc, uint32_t M, uint32_t N, uint32_t K) {
+    P5_REQUIRE(N % 8 == 0 && K % 8 == 0, P5_ERR_ARG, "GEMM N (%u) and K (%u) must be multiples of 8", N, K);
+    const bool f16_out = (epi == Epi::StoreF16 || epi == Epi::StoreF16Relu);
+    P5_REQUIRE((ldc * (f16_out ? 2u : 4u)) % 16 == 0, P5_ERR_ARG, "GEMM ldc (%u) breaks 16-byte row alignment", ldc);
+    P5_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0, P5_ERR_ARG, "GEMM output is not 16-byte aligned");
+    GemmShape s{M, N, K, ldc};
+    if (M == 0 || N == 0) return;
+    switch (variant) {
+        case 0: launch_epi<1, 256, 4>(stream, num_sms, epi, tma_a, tma_b, C, s); break;
+        case 1: launch_epi<2, 256, 6>(stream, num_sms, epi, tma_a, tma_b, C, s); break;
+        default: throw Error(P5_ERR_ARG, strf("unknown GEMM variant %d", variant));
+    }
+}
+
+void gemm_fp16(cudaStream_t stream, int num_sms, int variant, Epi epi, const void* A, uint32_t lda, const void* B,
+               uint32_t ldb, void* C, uint32_t ldc, uint32_t M, uint32_t N, uint32_t K) {
+    CUtensorMap ta = make_kmajor_tensor_map(A, M, K, lda, kGemmBlockM);
+    CUtensorMap tb = make_kmajor_tensor_map(B, N, K, ldb, gemm_b_box_rows(variant));
+    gemm_launch(stream, num_sms, variant, epi, ta, tb, C, ldc, M, N, K);
+}
+
+}  // namespace p5
