@@ -55,18 +55,20 @@ def _bind_optional(lib: C.CDLL) -> None:
     still loads for the symbol-export test, which reports what is missing)."""
     vp = C.c_void_p
     f32p = C.POINTER(C.c_float)
+    i32p, u32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_double)
     sigs = {
         "p5_model_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
         "p5_model_free": (None, [vp]),
-        "p5_model_info": (C.c_int, [vp, C.POINTER(C.c_uint32), C.c_int]),
-        "p5_predict": (C.c_int, [vp, vp, vp, C.c_uint64, vp, C.c_uint32]),
-        "p5_encode_debug": (C.c_int, [vp, vp, C.c_uint32, vp, vp]),
+        "p5_model_info": (C.c_int, [vp, u32p, C.c_int]),
+        "p5_token_table": (C.c_int, [vp, i32p]),
+        "p5_bias_table": (C.c_int, [vp, C.c_uint32, f32p]),
         "p5_set_option": (C.c_int, [vp, C.c_char_p, C.c_int64]),
-        "p5_stage": (C.c_int, [vp, vp, vp, C.c_uint64]),
+        "p5_predict": (C.c_int, [vp, vp, vp, C.c_uint64, vp, C.c_uint32]),
+        "p5_stage": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint32]),
         "p5_run_staged": (C.c_int, [vp, vp]),
-        "p5_get_stats": (C.c_int, [vp, C.POINTER(C.c_double), C.c_int]),
+        "p5_encode_debug": (C.c_int, [vp, vp, C.c_uint32, vp, vp, vp]),
+        "p5_get_stats": (C.c_int, [vp, f64p, C.c_int]),
         "p5_dbg_attention": (C.c_int, [C.c_int, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_int, f32p]),
-        "p5_dbg_rmsnorm": (C.c_int, [C.c_int, vp, vp, C.c_uint32, C.c_uint32, C.c_float, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name, None)

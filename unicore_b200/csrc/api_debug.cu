@@ -8,6 +8,7 @@
 #include "common.h"
 #include "gemm.cuh"
 #include "gemm_launch.h"
+#include "kernels.h"
 #include "prostt5_b200_debug.h"
 
 namespace p5 {
@@ -41,6 +42,7 @@ extern "C" int p5_dbg_gemm(int device, int variant, int epilogue, uint32_t M, ui
         P5_CUDA(cudaGetDeviceProperties(&prop, device));
         P5_REQUIRE(prop.major == 10, P5_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is sm_100a only", device,
                    prop.major, prop.minor);
+        gemm_init_device();
         const Epi epi = static_cast<Epi>(epilogue);
         const bool f16_out = (epi == Epi::StoreF16 || epi == Epi::StoreF16Relu);
         const size_t c_bytes = size_t(M) * N * (f16_out ? 2 : 4);
@@ -98,6 +100,7 @@ extern "C" int p5_dbg_gemm_bench(int device, int variant, int epilogue, uint32_t
         P5_CUDA(cudaGetDeviceProperties(&prop, device));
         P5_REQUIRE(prop.major == 10, P5_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is sm_100a only", device,
                    prop.major, prop.minor);
+        gemm_init_device();
         const Epi epi = static_cast<Epi>(epilogue);
         const bool f16_out = (epi == Epi::StoreF16 || epi == Epi::StoreF16Relu);
         const size_t c_bytes = size_t(M) * N * (f16_out ? 2 : 4);
@@ -122,6 +125,57 @@ extern "C" int p5_dbg_gemm_bench(int device, int variant, int epilogue, uint32_t
         *ms_out = ms / iters;
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
+        cudaStreamDestroy(st);
+    });
+}
+
+extern "C" int p5_dbg_attention(int device, const uint16_t* qkv_host, const int32_t* cu_host, uint32_t n_seq,
+                                uint32_t n_head, uint32_t max_dist, const float* bias_host, uint16_t* ctx_host, int iters,
+                                float* ms_out) {
+    return guarded([&] {
+        P5_REQUIRE(qkv_host && cu_host && bias_host && ctx_host && n_seq >= 1, P5_ERR_ARG, "null buffer");
+        P5_CUDA(cudaSetDevice(device));
+        attention_init_device();
+        const uint32_t M = uint32_t(cu_host[n_seq]);
+        const size_t inner = size_t(n_head) * kHeadDim;
+        std::vector<int2> work;
+        for (uint32_t s = 0; s < n_seq; ++s) {
+            const int T = cu_host[s + 1] - cu_host[s];
+            P5_REQUIRE(T >= 1, P5_ERR_ARG, "empty sequence %u", s);
+            for (int q = 0; q < T; q += int(kAttnBlockM)) work.push_back(make_int2(int(s), q));
+        }
+        DevBuf qkv(M * 3 * inner * 2), ctx(M * inner * 2), cu((n_seq + 1) * 4), wk(work.size() * sizeof(int2)),
+            bias(size_t(n_head) * (2 * max_dist + 1) * 4);
+        P5_CUDA(cudaMemcpy(qkv.p, qkv_host, M * 3 * inner * 2, cudaMemcpyHostToDevice));
+        P5_CUDA(cudaMemcpy(cu.p, cu_host, (n_seq + 1) * 4, cudaMemcpyHostToDevice));
+        P5_CUDA(cudaMemcpy(wk.p, work.data(), work.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        P5_CUDA(cudaMemcpy(bias.p, bias_host, size_t(n_head) * (2 * max_dist + 1) * 4, cudaMemcpyHostToDevice));
+        P5_CUDA(cudaMemset(ctx.p, 0, M * inner * 2));
+        cudaStream_t st;
+        P5_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        auto run = [&] {
+            launch_attention(st, static_cast<const __half*>(qkv.p), static_cast<__half*>(ctx.p),
+                             static_cast<const int32_t*>(cu.p), static_cast<const int2*>(wk.p), uint32_t(work.size()),
+                             static_cast<const float*>(bias.p), n_head, max_dist);
+        };
+        run();
+        P5_CUDA(cudaStreamSynchronize(st));
+        P5_CUDA(cudaMemcpy(ctx_host, ctx.p, M * inner * 2, cudaMemcpyDeviceToHost));
+        if (iters > 0 && ms_out) {
+            cudaEvent_t e0, e1;
+            P5_CUDA(cudaEventCreate(&e0));
+            P5_CUDA(cudaEventCreate(&e1));
+            for (int i = 0; i < 3; ++i) run();
+            P5_CUDA(cudaEventRecord(e0, st));
+            for (int i = 0; i < iters; ++i) run();
+            P5_CUDA(cudaEventRecord(e1, st));
+            P5_CUDA(cudaStreamSynchronize(st));
+            float ms = 0.f;
+            P5_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            *ms_out = ms / iters;
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
         cudaStreamDestroy(st);
     });
 }

@@ -58,12 +58,6 @@ void launch_one(cudaStream_t stream, int num_sms, const CUtensorMap& ta, const C
                 const GemmShape& s) {
     using L = GemmSmem<kCtaGroup, kBlockN, kStages>;
     auto kernel = gemm_tcgen05_kernel<kCtaGroup, kBlockN, kStages, kEpi>;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] {
-        attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kDynamic);
-    });
-    P5_CUDA(attr_err);
     const uint32_t num_mt = (s.M + kGemmBlockM * kCtaGroup - 1) / (kGemmBlockM * kCtaGroup);
     const uint32_t num_nt = (s.N + kBlockN - 1) / kBlockN;
     const uint32_t tiles = num_mt * num_nt;
@@ -96,7 +90,26 @@ void launch_epi(cudaStream_t stream, int num_sms, Epi epi, const CUtensorMap& ta
     }
 }
 
+template <int kCtaGroup, int kBlockN, int kStages>
+void init_variant() {
+    using L = GemmSmem<kCtaGroup, kBlockN, kStages>;
+    P5_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kCtaGroup, kBlockN, kStages, Epi::StoreF16>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kDynamic));
+    P5_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kCtaGroup, kBlockN, kStages, Epi::StoreF16Relu>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kDynamic));
+    P5_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kCtaGroup, kBlockN, kStages, Epi::AddF32>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kDynamic));
+    P5_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kCtaGroup, kBlockN, kStages, Epi::StoreF32>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kDynamic));
+}
+
 }  // namespace
+
+// Per-device one-time setup (function attributes are per device): call with the device current.
+void gemm_init_device() {
+    init_variant<1, 256, 4>();
+    init_variant<2, 256, 6>();
+}
 
 uint32_t gemm_b_box_rows(int variant) {
     switch (variant) {

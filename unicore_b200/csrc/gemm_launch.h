@@ -14,6 +14,7 @@ constexpr int kGemmVariantPair = 1;
 
 CUtensorMap make_kmajor_tensor_map(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 uint32_t gemm_b_box_rows(int variant);
+void gemm_init_device();  // once per device, with that device current
 
 // C[M,N] (op)= A[M,K] * B[N,K]^T with prebuilt tensor maps (weights keep theirs for the model lifetime)
 void gemm_launch(cudaStream_t stream, int num_sms, int variant, Epi epi, const CUtensorMap& tma_a,

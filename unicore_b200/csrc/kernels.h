@@ -1,0 +1,41 @@
+// Launchers of the non-GEMM sm_100a kernels of the ProstT5 path (SURVEY.md §2.4 K1,K2,K4,K8,K9,K10;
+// arithmetic spec §8a p2,p3,p5,p6,p9,p10,p11).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace p5 {
+
+// p2 + p3: h[t,:] = E[ids[t],:] (fp16 -> fp32 residual stream); xn = fp16(rmsnorm(h) * w)
+void launch_embed_rmsnorm(cudaStream_t st, const int32_t* ids, const __half* embd, const float* w, float eps, float* h,
+                          __half* xn, uint32_t M, uint32_t d, uint32_t n_vocab);
+
+// p3 / p9: xn = fp16(rmsnorm(h) * w); optionally also the fp32 value (debug / p5_encode_debug)
+void launch_rmsnorm(cudaStream_t st, const float* h, const float* w, float eps, __half* xn, float* out_f32, uint32_t M,
+                    uint32_t d);
+
+// p5 + p6: relative-position-bias attention over packed variable-length sequences.
+//   qkv   [M, 3*H*128] fp16: Q | K | V, head-major inside each third
+//   ctx   [M, H*128]   fp16
+//   cu    [S+1] token offsets of the sequences; work[n_work] = (seq, first query row of the 64-row tile)
+//   bias  [H, 2*max_dist+1] fp32: bias[h][clamp(j-i,-max_dist,max_dist)+max_dist]
+void launch_attention(cudaStream_t st, const __half* qkv, __half* ctx, const int32_t* cu, const int2* work,
+                      uint32_t n_work, const float* bias, uint32_t H, uint32_t max_dist);
+
+void attention_init_device();  // once per device, with that device current
+
+constexpr uint32_t kAttnBlockM = 64;  // query rows per attention work item
+constexpr uint32_t kHeadChunk = 64;   // residues per head work item
+constexpr uint32_t kHeadDim = 128;    // the attention kernel is specialised on ProstT5's d_kv
+
+// p10 + p11: taps [M, 7*C1] fp32 (tap-major: column t*C1 + c) -> relu conv0 -> conv1 -> argmax -> letter.
+//   work[n_work] = (seq, first residue of the chunk); residues of sequence s are head rows 0..L-1,
+//   head row r is token row cu[s] + 1 + r; include_eos adds the </s> row as head row L (conv input only).
+//   letters [sum L] at cu[s] - 2*s + r; logits_out (optional) [sum L, n_cls] fp32.
+void launch_head(cudaStream_t st, const float* taps, const int32_t* cu, const int2* work, uint32_t n_work,
+                 const float* b0, const float* w1, const float* b1, uint32_t c1, uint32_t n_cls, uint32_t ksize,
+                 int include_eos, uint8_t* letters, float* logits_out);
+
+}  // namespace p5
