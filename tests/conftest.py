@@ -1,0 +1,47 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with `-m gpu` on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def tiny_dir(tmp_path_factory):
+    """Weight directory with a synthetic TINY prostt5-f16.gguf (seed 7 = the seed of tests/golden)."""
+    from unicore_b200 import prostt5_spec as spec, synth
+    return synth.model_dir(str(tmp_path_factory.mktemp("p5_tiny")), spec.TINY, seed=7)
+
+
+@pytest.fixture(scope="session")
+def tiny_oracle(tiny_dir):
+    from oracle import prostt5_oracle as O
+    from unicore_b200 import prostt5_spec as spec
+    return O.load_gguf_model(os.path.join(tiny_dir, spec.WEIGHT_FILE))
+
+
+@pytest.fixture(scope="session")
+def full_dir():
+    """Synthetic full-size ProstT5 (2.4 GB, seed 1), cached under /tmp for the whole box lifetime."""
+    from unicore_b200 import prostt5_spec as spec, synth
+    return synth.model_dir(os.environ.get("P5_FULL_MODEL_DIR", "/tmp/p5_full_seed1"), spec.FULL, seed=1)
+
+
+@pytest.fixture(scope="session")
+def full_oracle(full_dir):
+    from oracle import prostt5_oracle as O
+    from unicore_b200 import prostt5_spec as spec
+    return O.load_gguf_model(os.path.join(full_dir, spec.WEIGHT_FILE))
+
+
+def random_protein(rng, L):
+    import numpy as np
+    from unicore_b200 import prostt5_spec as spec
+    letters = np.frombuffer(spec.AA_LETTERS.encode(), np.uint8)
+    return letters[rng.choice(20, size=L, p=spec.AA_FREQ / spec.AA_FREQ.sum())].tobytes()

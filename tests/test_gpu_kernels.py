@@ -1,0 +1,109 @@
+"""Kernel-level parity on the B200, through the C ABI (include/prostt5_b200_debug.h): the tcgen05 GEMM
+against a numpy fp32 product and the relative-bias attention against a numpy restatement of
+SURVEY.md §8a p5/p6 with the oracle's rounding policy."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from unicore_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(variant, epi, M, N, K, seed):
+    lib = _lib.load()
+    rng = np.random.default_rng(seed)
+    a = (rng.standard_normal((M, K), dtype=np.float32) * 0.5).astype(np.float16)
+    b = (rng.standard_normal((N, K), dtype=np.float32) * 0.5).astype(np.float16)
+    ref = a.astype(np.float32) @ b.astype(np.float32).T
+    if epi in (0, 1):
+        c = np.zeros((M, N), np.float16)
+        if epi == 1:
+            ref = np.maximum(ref, 0)
+    else:
+        c0 = rng.standard_normal((M, N), dtype=np.float32)
+        c = c0.copy()
+        ref = ref + c0 if epi == 2 else ref
+    ms = C.c_float(0)
+    _lib.check(lib.p5_dbg_gemm(0, variant, epi, M, N, K, a.ctypes.data, b.ctypes.data, c.ctypes.data, 0, C.byref(ms)))
+    return c.astype(np.float32), ref
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("epi,M,N,K", [
+    (0, 128, 256, 64),        # one tile, one k-block
+    (0, 1, 8, 8),             # smallest legal problem
+    (3, 300, 264, 200),       # ragged M, N and K: zero-filled tails, masked stores
+    (1, 1000, 512, 256),      # ReLU epilogue (FFN-in)
+    (2, 777, 1024, 4096),     # fp32 residual add (O projection shape)
+    (0, 2100, 12288, 1024),   # QKV shape, several tiles per CTA
+    (2, 515, 1024, 16384),    # FFN-out shape: 256 k-blocks
+    (3, 2048, 224, 1024),     # conv-head taps shape
+])
+def test_gemm_matches_numpy(variant, epi, M, N, K):
+    got, ref = _gemm(variant, epi, M, N, K, seed=M * 7 + N * 3 + K + epi)
+    f16_out = epi in (0, 1)
+    # fp32 accumulation: only the summation order differs; fp16 outputs add one rounding (2^-11 relative)
+    tol = (1.0 / 1024 if f16_out else 1e-5) * np.abs(ref) + 2e-4 * np.sqrt(K)
+    assert (np.abs(got - ref) <= tol).all(), float(np.abs(got - ref).max())
+
+
+def test_gemm_is_deterministic():
+    a, _ = _gemm(1, 0, 1000, 512, 1024, seed=5)
+    b, _ = _gemm(1, 0, 1000, 512, 1024, seed=5)
+    np.testing.assert_array_equal(a, b)
+
+
+def _attention_ref(qkv, cu, H, bias, md):
+    D = 128
+    out = np.zeros((qkv.shape[0], H * D), np.float32)
+    q32 = qkv.astype(np.float32)
+    for s in range(len(cu) - 1):
+        a, b = int(cu[s]), int(cu[s + 1])
+        pos = np.arange(b - a)
+        dl = np.clip(pos[None, :] - pos[:, None], -md, md) + md
+        for h in range(H):
+            q = q32[a:b, h * D:(h + 1) * D]
+            k = q32[a:b, (H + h) * D:(H + h + 1) * D]
+            v = q32[a:b, (2 * H + h) * D:(2 * H + h + 1) * D]
+            sc = q @ k.T + bias[h][dl]  # no 1/sqrt(d)
+            e = np.exp(sc - sc.max(-1, keepdims=True))
+            out[a:b, h * D:(h + 1) * D] = (e.astype(np.float16).astype(np.float32) @ v) / e.sum(-1, keepdims=True)
+    return out
+
+
+@pytest.mark.parametrize("lens,H", [([1], 1), ([3], 1), ([64], 2), ([65, 1, 130], 2), ([352, 352], 4),
+                                    ([700, 66, 1026], 2), ([2500], 1)])
+def test_attention_matches_numpy(lens, H):
+    lib = _lib.load()
+    rng = np.random.default_rng(sum(lens) + H)
+    cu = np.zeros(len(lens) + 1, np.int32)
+    cu[1:] = np.cumsum(lens)
+    M, md = int(cu[-1]), 128
+    qkv = (rng.standard_normal((M, 3 * H * 128), dtype=np.float32) * 0.6).astype(np.float16)
+    bias = (rng.standard_normal((H, 2 * md + 1), dtype=np.float32) * 0.5).astype(np.float32)
+    ctx = np.zeros((M, H * 128), np.float16)
+    ms = C.c_float(0)
+    _lib.check(lib.p5_dbg_attention(0, qkv.ctypes.data, cu.ctypes.data, len(lens), H, md, bias.ctypes.data,
+                                    ctx.ctypes.data, 0, C.byref(ms)))
+    ref = _attention_ref(qkv, cu, H, bias, md)
+    # tolerance: ctx is stored fp16 (2^-11 relative) + fp16 rounding of P against a different running max
+    assert np.abs(ctx.astype(np.float32) - ref).max() < 4e-3
+
+
+def test_attention_peaked_scores():
+    """Un-scaled T5 scores can be large: one dominant key per row must not overflow or lose the row."""
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    T, H, md = 200, 1, 128
+    cu = np.array([0, T], np.int32)
+    qkv = (rng.standard_normal((T, 3 * 128), dtype=np.float32) * 3.0).astype(np.float16)  # |q.k| up to ~1000
+    bias = np.zeros((H, 2 * md + 1), np.float32)
+    ctx = np.zeros((T, 128), np.float16)
+    ms = C.c_float(0)
+    _lib.check(lib.p5_dbg_attention(0, qkv.ctypes.data, cu.ctypes.data, 1, H, md, bias.ctypes.data, ctx.ctypes.data, 0,
+                                    C.byref(ms)))
+    ref = _attention_ref(qkv, cu, H, bias, md)
+    assert np.isfinite(ctx.astype(np.float32)).all()
+    assert np.abs(ctx.astype(np.float32) - ref).max() < 2e-2

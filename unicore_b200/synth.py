@@ -45,7 +45,13 @@ def make_tensor(name: str, shape: tuple, dtype: str, cfg: spec.ProstT5Config, se
         if kind == "norm":
             x += np.float32(1.0)
         out[s:s + len(x)] = x
-    return out.reshape(shape)
+    out = out.reshape(shape)
+    if name == "cnn.conv1.weight":
+        # zero-sum filters per class: conv0's ReLU output is non-negative, so a class whose weights sum
+        # high would win almost every residue; centring makes the 20 letters comparably frequent
+        x = out.astype(np.float32)
+        out = (x - x.mean(axis=(1, 2), keepdims=True)).astype(out.dtype)
+    return out
 
 
 def make_weights(cfg: spec.ProstT5Config, seed: int = 1) -> dict:
