@@ -187,8 +187,7 @@ def test_config2_properties(full):
     c = full.predict_packed(aa, off)
     full.set_option("max_batch_tokens", 94720)
     np.testing.assert_array_equal(a, c)
+    assert full.stats()["residues"] == 89600
     for i in (0, 100, 255):
         s = aa[int(off[i]):int(off[i + 1])].tobytes()
         assert full.encode_debug(s)[2] == a[int(off[i]):int(off[i + 1])].tobytes()
-    st = full.stats()
-    assert st["residues"] == 89600

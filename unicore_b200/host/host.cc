@@ -1,0 +1,375 @@
+#include "host.h"
+
+#include <dirent.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <unordered_map>
+
+#include "md5.h"
+#include "prostt5_b200.h"
+
+namespace ub {
+
+int g_verbosity = 3;
+
+void msg(int level, const std::string& s) {
+    if (g_verbosity >= level) {
+        fputs(s.c_str(), stdout);
+        fputc('\n', stdout);
+        fflush(stdout);
+    }
+}
+
+void die(int code, const std::string& what) {
+    const char* label = "Unknown error";
+    switch (code) {  // [REF src/envs/error_handler.rs:17-33]
+        case ERR_GENERAL: label = "Error: "; break;
+        case ERR_FILE_NOT_FOUND: label = "File not found: "; break;
+        case ERR_FILE_INVALID: label = "Invalid file given: "; break;
+        case ERR_BINARY_NOT_FOUND: label = "Binary not found: "; break;
+        case ERR_MODULE_NOT_IMPLEMENTED: label = "Module not implemented: "; break;
+        case ERR_ARGPARSE: label = "Argument parsing error: "; break;
+        case ERR_OUTPUT_EXISTS: label = "Output file already exists: "; break;
+    }
+    if (g_verbosity >= 1) fprintf(stderr, "%s%s\n", label, what.c_str());
+    exit(code);
+}
+
+bool path_exists(const std::string& p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0;
+}
+bool is_dir(const std::string& p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+bool is_file(const std::string& p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode);
+}
+std::string base_name(const std::string& p) {
+    std::string s = p;
+    while (s.size() > 1 && s.back() == '/') s.pop_back();
+    const size_t k = s.rfind('/');
+    return k == std::string::npos ? s : s.substr(k + 1);
+}
+std::string parent_dir(const std::string& p) {
+    std::string s = p;
+    while (s.size() > 1 && s.back() == '/') s.pop_back();
+    const size_t k = s.rfind('/');
+    if (k == std::string::npos) return "";
+    if (k == 0) return "/";
+    return s.substr(0, k);
+}
+std::string file_stem(const std::string& p) {
+    const std::string b = base_name(p);
+    const size_t k = b.rfind('.');
+    return (k == std::string::npos || k == 0) ? b : b.substr(0, k);
+}
+static std::string extension(const std::string& p) {
+    const std::string b = base_name(p);
+    const size_t k = b.rfind('.');
+    return (k == std::string::npos || k == 0) ? "" : b.substr(k + 1);
+}
+void mkdir_p(const std::string& p) {
+    if (p.empty() || is_dir(p)) return;
+    mkdir_p(parent_dir(p));
+    if (mkdir(p.c_str(), 0777) != 0 && !is_dir(p)) die(ERR_GENERAL, "Could not create directory " + p);
+}
+
+// Rust's BufRead::lines(): split at '\n', drop one trailing '\r'; lines that are not valid UTF-8 are
+// errors and are skipped by the reference's filter_map(|l| l.ok()).
+static bool valid_utf8(const std::string& s) {
+    size_t i = 0;
+    const size_t n = s.size();
+    while (i < n) {
+        const unsigned char c = s[i];
+        size_t len;
+        uint32_t cp;
+        if (c < 0x80) { ++i; continue; }
+        else if ((c & 0xE0) == 0xC0) { len = 2; cp = c & 0x1F; }
+        else if ((c & 0xF0) == 0xE0) { len = 3; cp = c & 0x0F; }
+        else if ((c & 0xF8) == 0xF0) { len = 4; cp = c & 0x07; }
+        else return false;
+        if (i + len > n) return false;
+        for (size_t k = 1; k < len; ++k) {
+            const unsigned char d = s[i + k];
+            if ((d & 0xC0) != 0x80) return false;
+            cp = (cp << 6) | (d & 0x3F);
+        }
+        if ((len == 2 && cp < 0x80) || (len == 3 && cp < 0x800) || (len == 4 && (cp < 0x10000 || cp > 0x10FFFF)) ||
+            (cp >= 0xD800 && cp <= 0xDFFF))
+            return false;
+        i += len;
+    }
+    return true;
+}
+
+template <class F>
+static void for_each_line(const std::string& path, F&& fn) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) die(ERR_GENERAL, "Unable to open file " + path);
+    std::string line;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        fn(line);
+    }
+}
+
+std::vector<std::pair<std::string, std::string>> read_fasta(const std::string& path) {
+    std::vector<std::pair<std::string, std::string>> out;
+    std::unordered_map<std::string, size_t> pos;
+    auto insert = [&](const std::string& h, const std::string& s) {
+        auto it = pos.find(h);
+        if (it == pos.end()) {
+            pos[h] = out.size();
+            out.emplace_back(h, s);
+        } else {
+            out[it->second].second = s;
+        }
+    };
+    std::string header, seq;
+    for_each_line(path, [&](const std::string& line) {
+        if (!valid_utf8(line)) return;
+        if (!line.empty() && line[0] == '>') {
+            if (!header.empty()) {
+                insert(header, seq);
+                seq.clear();
+            }
+            header = line.substr(1);
+        } else {
+            seq += line;
+        }
+    });
+    insert(header, seq);
+    return out;
+}
+
+// Unicode White_Space code points (char::is_whitespace)
+static bool is_ws_cp(uint32_t cp) {
+    return (cp >= 0x09 && cp <= 0x0D) || cp == 0x20 || cp == 0x85 || cp == 0xA0 || cp == 0x1680 ||
+           (cp >= 0x2000 && cp <= 0x200A) || cp == 0x2028 || cp == 0x2029 || cp == 0x202F || cp == 0x205F || cp == 0x3000;
+}
+
+std::string sanitize_header(const std::string& key) {
+    std::string out;
+    size_t i = 0;
+    const size_t n = key.size();
+    while (i < n) {
+        const unsigned char c = key[i];
+        size_t len = 1;
+        uint32_t cp = c;
+        if (c >= 0x80) {
+            if ((c & 0xE0) == 0xC0) { len = 2; cp = c & 0x1F; }
+            else if ((c & 0xF0) == 0xE0) { len = 3; cp = c & 0x0F; }
+            else if ((c & 0xF8) == 0xF0) { len = 4; cp = c & 0x07; }
+            if (i + len > n) len = 1;
+            for (size_t k = 1; k < len; ++k) cp = (cp << 6) | (static_cast<unsigned char>(key[i + k]) & 0x3F);
+        }
+        const bool repl = is_ws_cp(cp) || cp == ';' || cp == ':' || cp == ',' || cp == '=' || cp == '/' || cp == '(' || cp == ')';
+        if (repl) out.push_back('_');
+        else out.append(key, i, len);
+        i += len;
+    }
+    return out;
+}
+
+std::string hashed_name(const std::string& seq) { return "unicore_" + Md5::of(seq).substr(0, 10); }
+
+std::vector<Record> collect_records(const std::string& input, const std::string& map_path, long max_len) {
+    std::vector<std::string> files;
+    if (is_dir(input)) {
+        DIR* d = opendir(input.c_str());
+        if (!d) die(ERR_GENERAL, "Could not read directory " + input);
+        while (dirent* e = readdir(d)) {
+            const std::string name = e->d_name;
+            const std::string full = input + (input.back() == '/' ? "" : "/") + name;
+            const std::string ext = extension(name);
+            if (is_file(full) && (ext == "fasta" || ext == "fa")) files.push_back(full);
+        }
+        closedir(d);
+        std::sort(files.begin(), files.end());  // read_dir order is unspecified; sorted here for reproducible output
+    } else {
+        if (!is_file(input)) die(ERR_GENERAL, "Input is not a directory or a file");
+        files.push_back(input);
+    }
+    std::ofstream map(map_path, std::ios::binary);
+    if (!map) die(ERR_GENERAL, "Could not create " + map_path);
+    std::vector<Record> recs;
+    std::unordered_map<std::string, size_t> seen;
+    for (const std::string& f : files) {
+        const std::string species = file_stem(f);
+        for (auto& kv : read_fasta(f)) {
+            const std::string& value = kv.second;
+            if (max_len >= 0 && value.size() > size_t(max_len)) continue;
+            if (value.size() < 2) {
+                msg(3, "Skipping " + kv.first + " as it is too short");
+                continue;
+            }
+            const std::string key = sanitize_header(kv.first);
+            const std::string name = hashed_name(value);
+            auto it = seen.find(name);
+            if (it == seen.end()) {
+                seen[name] = recs.size();
+                recs.push_back({name, value});
+            } else {
+                recs[it->second].seq = value;  // HashMap insert: a 40-bit prefix collision keeps the last sequence
+            }
+            map << name << '\t' << species << '\t' << key << '\n';
+        }
+    }
+    map.flush();
+    if (!map) die(ERR_GENERAL, "Could not write " + map_path);
+    return recs;
+}
+
+void write_fasta(const std::string& path, const std::vector<Record>& recs) {
+    std::ofstream out(path, std::ios::binary);
+    if (!out) die(ERR_GENERAL, "Could not create " + path);
+    for (const Record& r : recs) out << '>' << r.name << '\n' << r.seq << '\n';
+    out.flush();
+    if (!out) die(ERR_GENERAL, "Could not write " + path);
+}
+
+std::vector<Record> read_fasta_records(const std::string& path) {
+    std::vector<Record> recs;
+    bool have = false;
+    Record cur;
+    for_each_line(path, [&](const std::string& line) {
+        if (!line.empty() && line[0] == '>') {
+            if (have) recs.push_back(cur);
+            cur = Record{line.substr(1), ""};
+            have = true;
+        } else if (have) {
+            for (char c : line)
+                if (!isspace(static_cast<unsigned char>(c))) cur.seq.push_back(c);
+        }
+    });
+    if (have) recs.push_back(cur);
+    return recs;
+}
+
+static void write_dbtype(const std::string& path, int32_t type) {
+    std::ofstream out(path, std::ios::binary);
+    out.write(reinterpret_cast<const char*>(&type), 4);  // little-endian host
+    out.flush();
+    if (!out) die(ERR_GENERAL, "Could not write " + path);
+}
+
+template <class F>
+static void write_one_db(const std::string& db, size_t n, int32_t dbtype, F&& payload) {
+    std::ofstream data(db, std::ios::binary);
+    std::ofstream index(db + ".index", std::ios::binary);
+    if (!data || !index) die(ERR_GENERAL, "Could not create database " + db);
+    uint64_t off = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const std::string& p = payload(i);
+        data.write(p.data(), std::streamsize(p.size()));
+        data.write("\n\0", 2);
+        const uint64_t len = p.size() + 2;
+        index << i << '\t' << off << '\t' << len << '\n';
+        off += len;
+    }
+    data.flush();
+    index.flush();
+    if (!data || !index) die(ERR_GENERAL, "Could not write database " + db);
+    write_dbtype(db + ".dbtype", dbtype);
+}
+
+void write_foldseek_db(const std::string& db, const std::vector<Record>& recs, const std::vector<std::string>& ss,
+                       const std::string& source_name) {
+    if (recs.size() != ss.size()) die(ERR_GENERAL, "internal: 3Di count differs from the record count");
+    for (size_t i = 0; i < recs.size(); ++i)
+        if (recs[i].seq.size() != ss[i].size()) die(ERR_GENERAL, "internal: 3Di length differs for " + recs[i].name);
+    constexpr int32_t kAminoAcids = 0, kGeneric = 12;  // MMseqs2 Parameters::DBTYPE_*
+    write_one_db(db, recs.size(), kAminoAcids, [&](size_t i) -> const std::string& { return recs[i].seq; });
+    write_one_db(db + "_ss", recs.size(), kAminoAcids, [&](size_t i) -> const std::string& { return ss[i]; });
+    write_one_db(db + "_h", recs.size(), kGeneric, [&](size_t i) -> const std::string& { return recs[i].name; });
+    std::ofstream lookup(db + ".lookup", std::ios::binary);
+    for (size_t i = 0; i < recs.size(); ++i) {
+        const std::string& h = recs[i].name;
+        size_t e = 0;
+        while (e < h.size() && !isspace(static_cast<unsigned char>(h[e]))) ++e;
+        lookup << i << '\t' << h.substr(0, e) << '\t' << 0 << '\n';
+    }
+    std::ofstream source(db + ".source", std::ios::binary);
+    source << 0 << '\t' << source_name << '\n';
+    lookup.flush();
+    source.flush();
+    if (!lookup || !source) die(ERR_GENERAL, "Could not write lookup/source of " + db);
+}
+
+std::vector<std::string> read_db(const std::string& path) {
+    std::vector<std::string> out;
+    std::ifstream in(path, std::ios::binary);
+    if (!in) die(ERR_GENERAL, "Unable to read db " + path);
+    std::string line;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (!line.empty() && line[0] == '\0') line.erase(0, 1);
+        if (!line.empty()) out.push_back(line);
+    }
+    return out;
+}
+
+void write_checkpoint(const std::string& path, const std::string& content) {
+    std::ofstream out(path, std::ios::binary | std::ios::trunc);
+    out << content;
+    out.flush();
+    if (!out) die(ERR_GENERAL, "Could not write checkpoint " + path);
+}
+std::string read_checkpoint(const std::string& path) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) die(ERR_GENERAL, "Could not read checkpoint " + path);
+    return std::string((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+}
+
+std::vector<std::string> predict_3di(const std::string& model_dir, const std::vector<Record>& recs,
+                                     const PredictOptions& opt) {
+    using clk = std::chrono::steady_clock;
+    std::vector<int> devs = opt.devices;
+    p5_model* m = nullptr;
+    const auto t0 = clk::now();
+    if (p5_model_load(model_dir.c_str(), devs.empty() ? nullptr : devs.data(), devs.empty() ? -1 : int(devs.size()), &m) != 0)
+        die(ERR_GENERAL, std::string("ProstT5 model: ") + p5_last_error());
+    const auto t1 = clk::now();
+    if (opt.max_batch_tokens > 0 && p5_set_option(m, "max_batch_tokens", opt.max_batch_tokens) != 0)
+        die(ERR_GENERAL, p5_last_error());
+    std::vector<uint64_t> off(recs.size() + 1, 0);
+    for (size_t i = 0; i < recs.size(); ++i) off[i + 1] = off[i] + recs[i].seq.size();
+    std::string aa;
+    aa.reserve(off.back());
+    for (const Record& r : recs) aa += r.seq;
+    std::string out(aa.size(), '\0');
+    if (p5_predict(m, reinterpret_cast<const uint8_t*>(aa.data()), off.data(), recs.size(),
+                   reinterpret_cast<uint8_t*>(&out[0]), opt.split_len) != 0)
+        die(ERR_GENERAL, std::string("ProstT5 prediction failed: ") + p5_last_error());
+    const auto t2 = clk::now();
+    double st[14] = {0};
+    p5_get_stats(m, st, 14);
+    p5_model_free(m);
+    std::vector<std::string> ss(recs.size());
+    for (size_t i = 0; i < recs.size(); ++i) ss[i] = out.substr(off[i], off[i + 1] - off[i]);
+    const double load_s = std::chrono::duration<double>(t1 - t0).count();
+    const double pred_s = std::chrono::duration<double>(t2 - t1).count();
+    msg(3, "ProstT5: " + std::to_string(recs.size()) + " sequences, " + std::to_string(off.back()) + " residues in " +
+               std::to_string(pred_s) + " s (" + std::to_string(off.back() / std::max(pred_s, 1e-9)) +
+               " residues/s; weights loaded in " + std::to_string(load_s) + " s)");
+    if (!opt.stats_json.empty()) {
+        std::ofstream js(opt.stats_json);
+        js << "{\"sequences\": " << recs.size() << ", \"residues\": " << off.back() << ", \"predict_seconds\": " << pred_s
+           << ", \"load_seconds\": " << load_s << ", \"residues_per_second\": " << off.back() / std::max(pred_s, 1e-9)
+           << ", \"batches\": " << st[0] << ", \"tokens\": " << st[1] << ", \"kernel_launches\": " << st[3]
+           << ", \"device_ms_max\": " << st[4] << "}\n";
+    }
+    return ss;
+}
+
+}  // namespace ub

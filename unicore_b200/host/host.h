@@ -1,0 +1,79 @@
+// Host side of `unicore createdb` in C++ (the reference's is Rust; no Rust toolchain exists in this
+// image): FASTA parsing, record naming, .map file, checkpoint, MMseqs/Foldseek DB writer.  Each function
+// cites the reference code whose behaviour it keeps.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace ub {
+
+// error codes of the reference CLI [REF src/envs/error_handler.rs:5-14]
+enum : int {
+    ERR_GENERAL = 0x01, ERR_FILE_NOT_FOUND = 0x10, ERR_FILE_INVALID = 0x11, ERR_BINARY_NOT_FOUND = 0x20,
+    ERR_MODULE_NOT_IMPLEMENTED = 0x30, ERR_ARGPARSE = 0x40, ERR_OUTPUT_EXISTS = 0x50,
+};
+
+extern int g_verbosity;  // 0 quiet, 1 +errors, 2 +warnings, 3 +info, 4 +debug [REF src/util/message.rs:4-22]
+void msg(int level, const std::string& s);                 // stdout when verbosity >= level
+[[noreturn]] void die(int code, const std::string& what);  // "<label>: what" on stderr, exit(code)
+
+// [REF src/seq/fasta_io.rs:6-25] records in first-appearance order; a repeated header keeps its first
+// position and takes the LAST sequence (HashMap insert semantics); the trailing record is always
+// inserted, so an empty file yields one ("", "") record.
+std::vector<std::pair<std::string, std::string>> read_fasta(const std::string& path);
+
+// [REF src/modules/createdb.rs:15-18,101] whitespace (Unicode White_Space) ; : , = / ( ) -> '_'
+std::string sanitize_header(const std::string& key);
+
+// [REF src/modules/createdb.rs:104-106]
+std::string hashed_name(const std::string& seq);
+
+struct Record {  // one DB entry
+    std::string name;  // header line without '>'
+    std::string seq;
+};
+
+// [REF src/modules/createdb.rs:68-111] input listing, length filters, naming, de-duplication, .map file.
+// Returns the unique records in first-appearance order.
+std::vector<Record> collect_records(const std::string& input, const std::string& map_path, long max_len);
+
+// [REF src/seq/fasta_io.rs:27-48] ">name\nseq\n"
+void write_fasta(const std::string& path, const std::vector<Record>& recs);
+
+// plain FASTA reader for the foldseek-argv shim (every record kept, in file order)
+std::vector<Record> read_fasta_records(const std::string& path);
+
+// MMseqs2/Foldseek sequence DB triple <db>, <db>_h, <db>_ss (+ .index, .dbtype, .lookup, .source)
+// (SURVEY.md §8a row DBW); entries share one physical order in the three data files, which is what the
+// reference's reader relies on [REF src/seq/create_gene_specific_fasta.rs:9-44].
+void write_foldseek_db(const std::string& db, const std::vector<Record>& recs, const std::vector<std::string>& ss,
+                       const std::string& source_name);
+
+// [REF src/seq/create_gene_specific_fasta.rs:9-25]
+std::vector<std::string> read_db(const std::string& path);
+
+// [REF src/util/checkpoint.rs:2-10]
+void write_checkpoint(const std::string& path, const std::string& content);
+std::string read_checkpoint(const std::string& path);
+
+bool path_exists(const std::string& p);
+bool is_dir(const std::string& p);
+bool is_file(const std::string& p);
+std::string parent_dir(const std::string& p);  // Rust Path::parent(): "" for a bare file name
+std::string file_stem(const std::string& p);
+std::string base_name(const std::string& p);
+void mkdir_p(const std::string& p);
+
+// runs the predictor over the records: returns one 3Di string per record (calls the C ABI)
+struct PredictOptions {
+    std::vector<int> devices;  // empty = every visible device
+    uint32_t split_len = 0;
+    int64_t max_batch_tokens = 0;  // 0 = library default
+    std::string stats_json;        // optional path
+};
+std::vector<std::string> predict_3di(const std::string& model_dir, const std::vector<Record>& recs,
+                                     const PredictOptions& opt);
+
+}  // namespace ub
