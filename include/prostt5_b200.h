@@ -42,7 +42,8 @@ extern "C" {
 
 typedef struct p5_model p5_model; /* opaque: weights replicated on 1..N devices + per-device workspaces */
 
-/* Loads `<model_dir>/prostt5-f16.gguf` onto every device in `devices` (n_devices >= 1; NULL = device 0).
+/* Loads `<model_dir>/prostt5-f16.gguf` onto every device in `devices` (n_devices >= 1; NULL or 0 = device 0;
+ * n_devices < 0 = every visible device).
  * Fails with P5_ERR_FORMAT if the directory holds the retired safetensors layout
  * (cnn.safetensors or model/cnn.safetensors) and with P5_ERR_IO if the gguf is missing. */
 int p5_model_load(const char* model_dir, const int* devices, int n_devices, p5_model** out);

@@ -1,0 +1,89 @@
+"""Drop-in check on the B200: the C++ `unicore-b200 createdb` CLI and the foldseek argv shim produce a
+Foldseek DB triple that the reference's consumers accept (restated read_db + MMseqs invariants), with
+3Di strings equal to the oracle's (margin policy of test_gpu_model.py)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import random_protein
+from oracle import host_oracle as H, prostt5_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+UNICORE = os.path.join(ROOT, "unicore_b200", "bin", "unicore-b200")
+SHIM = os.path.join(ROOT, "unicore_b200", "bin", "foldseek-b200")
+
+
+def _write_proteomes(d, rng):
+    d.mkdir()
+    seqs = {}
+    for sp in ("Alpha_one", "Beta_two", "Gamma.three"):
+        lines = []
+        for k in range(12):
+            s = random_protein(rng, int(rng.integers(2, 500))).decode()
+            seqs[f"{sp}|{k}"] = s
+            lines.append(f">tr|{sp}|{k} some protein (x) OS=Y\n" + "\n".join(s[i:i + 60] for i in range(0, len(s), 60)) + "\n")
+        lines.append(">tiny\nM\n")
+        (d / f"{sp}.fa").write_text("".join(lines))
+    return seqs
+
+
+def _check_ss(entries, om):
+    bad = 0
+    for name, aa, ss in entries:
+        want, logits, _ = om.predict(aa.encode())
+        decided = O.top2_margin(logits) > 2e-2
+        a, b = np.frombuffer(ss.encode(), np.uint8), np.frombuffer(want, np.uint8)
+        assert (a[decided] == b[decided]).all(), name
+        bad += int((a != b).sum())
+    return bad
+
+
+def test_unicore_createdb_end_to_end(tmp_path, tiny_dir, tiny_oracle):
+    rng = np.random.default_rng(5)
+    seqs = _write_proteomes(tmp_path / "in", rng)
+    out = tmp_path / "res" / "proteome" / "proteome_db"
+    stats = tmp_path / "stats.json"
+    p = subprocess.run([UNICORE, "createdb", str(tmp_path / "in"), str(out), tiny_dir, "-g", "--threads", "4",
+                        "--max-batch-tokens", "3000", "--stats-json", str(stats)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert (out.parent / "createdb.chk").read_text() == "1"
+    assert not (out.parent / "combined_aa.fasta").exists()  # removed without --keep [REF createdb.rs:208-210]
+    entries = H.check_foldseek_db(str(out))
+    assert len(entries) == 36
+    assert sorted(aa for _, aa, _ in entries) == sorted(seqs.values())
+    assert all(name == H.hashed_name(aa) for name, aa, _ in entries)
+    _check_ss(entries, tiny_oracle)
+    # .map: one line per kept input record, names resolve into the DB (what `profile`/`tree` rely on)
+    rows = [l.split("\t") for l in open(str(out) + ".map").read().splitlines()]
+    assert len(rows) == 36 and {r[0] for r in rows} == {n for n, _, _ in entries}
+    assert {r[1] for r in rows} == {"Alpha_one", "Beta_two", "Gamma.three"}
+    assert "residues_per_second" in stats.read_text()
+    # second run without -o refuses; with -o it rebuilds the same DB
+    p2 = subprocess.run([UNICORE, "createdb", str(tmp_path / "in"), str(out), tiny_dir], capture_output=True, text=True)
+    assert p2.returncode == 1 and "Database already exists" in p2.stderr
+    before = open(str(out) + "_ss", "rb").read()
+    p3 = subprocess.run([UNICORE, "createdb", str(tmp_path / "in"), str(out), tiny_dir, "-o", "-k"], capture_output=True, text=True)
+    assert p3.returncode == 0 and open(str(out) + "_ss", "rb").read() == before
+    assert (out.parent / "combined_aa.fasta").exists()
+
+
+def test_foldseek_shim_createdb(tmp_path, tiny_dir, tiny_oracle):
+    """The argv an unmodified reference sends [REF src/modules/createdb.rs:158-166]."""
+    rng = np.random.default_rng(6)
+    recs = [(H.hashed_name(s), s) for s in (random_protein(rng, int(L)).decode() for L in (2, 40, 333, 64, 65))]
+    fasta = tmp_path / "combined_aa.fasta"
+    fasta.write_text("".join(f">{n}\n{s}\n" for n, s in recs))
+    db = tmp_path / "db"
+    p = subprocess.run([SHIM, "createdb", str(fasta), str(db), "--prostt5-model", tiny_dir, "--threads", "8", "--gpu", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    entries = H.check_foldseek_db(str(db))
+    assert [(n, a) for n, a, _ in entries] == recs
+    _check_ss(entries, tiny_oracle)
+    p = subprocess.run([SHIM, "createdb", str(fasta), str(db), "--prostt5-model", str(tmp_path / "nope")],
+                       capture_output=True, text=True)
+    assert p.returncode == 1 and "prostt5-f16.gguf" in p.stderr

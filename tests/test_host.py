@@ -1,0 +1,168 @@
+"""The C++ host side (unicore_b200/host) against the Python restatement of the reference's Rust
+(oracle/host_oracle.py) and against known answers.  No GPU: the CLI is driven up to the point where it
+needs the device (which must fail loudly), everything before that is checked."""
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+from oracle import host_oracle as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "unicore_b200", "bin")
+UNICORE = os.path.join(BIN, "unicore-b200")
+SHIM = os.path.join(BIN, "foldseek-b200")
+
+
+@pytest.fixture(scope="module")
+def hostlib():
+    path = os.path.join(ROOT, "unicore_b200", "lib", "libunicore_host.so")
+    assert os.path.exists(path), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = C.CDLL(path)
+    for f in ("ubh_md5_hex", "ubh_hashed_name", "ubh_sanitize_header"):
+        getattr(lib, f).restype = C.c_size_t
+        getattr(lib, f).argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    lib.ubh_read_fasta.restype = C.c_size_t
+    lib.ubh_read_fasta.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    return lib
+
+
+def _call(fn, data: bytes) -> str:
+    buf = C.create_string_buffer(4 * len(data) + 64)
+    n = fn(data, len(data), buf, len(buf))
+    return buf.raw[:n].decode("utf-8")
+
+
+def test_md5_rfc1321_vectors(hostlib):
+    kat = {b"": "d41d8cd98f00b204e9800998ecf8427e", b"a": "0cc175b9c0f1b6a831c399e269772661",
+           b"abc": "900150983cd24fb0d6963f7d28e17f72", b"message digest": "f96b697d7cb7938d525a2f31aaf161d0",
+           b"abcdefghijklmnopqrstuvwxyz": "c3fcd3d76192e4007dfb496cca67e13b",
+           b"12345678901234567890123456789012345678901234567890123456789012345678901234567890":
+               "57edf4a22be3c955ac49da2e2107b67a"}
+    for msg, want in kat.items():
+        assert _call(hostlib.ubh_md5_hex, msg) == want
+    for n in (55, 56, 57, 63, 64, 65, 119, 120, 1000, 100003):  # padding boundaries, multi-block
+        msg = bytes((i * 131 + 7) & 0xFF for i in range(n))
+        assert _call(hostlib.ubh_md5_hex, msg) == hashlib.md5(msg).hexdigest()
+
+
+def test_names_and_sanitiser(hostlib):
+    seqs = [b"MK", b"MKTAYIAKQRQISFVKSHFSRQ", b"ACDEFGHIKLMNPQRSTVWY" * 50]
+    for s in seqs:
+        assert _call(hostlib.ubh_hashed_name, s) == H.hashed_name(s.decode())
+    assert H.hashed_name("MK") == "unicore_" + hashlib.md5(b"MK").hexdigest()[:10]
+    heads = ["tr|A0A370ARU3|A0A370ARU3_9SPIO Septum formation (initiator) OS=Ocean sp. M1 OX=2283433 GN=DV872_14820",
+             "a;b:c,d=e/f(g)h\ti", "nbsp thin ideo　line end", "plain_name", "", "trailing ",
+             "café über=中文"]
+    for h in heads:
+        assert _call(hostlib.ubh_sanitize_header, h.encode()) == H.sanitize_header(h)
+    assert H.sanitize_header("a b;c:d,e=f/g(h)i") == "a_b_c_d_e_f_g_h_i"
+
+
+def _read_fasta_cpp(hostlib, path):
+    need = C.c_size_t(0)
+    buf = C.create_string_buffer(1 << 20)
+    n = hostlib.ubh_read_fasta(path.encode(), buf, len(buf), C.byref(need))
+    parts = buf.raw[:need.value].split(b"\0")[:-1]
+    assert len(parts) == 2 * n
+    return [(parts[2 * i].decode(), parts[2 * i + 1].decode()) for i in range(n)]
+
+
+@pytest.mark.parametrize("content", [
+    b">a desc\nMKT\nAYI\n>b\nGG\n",
+    b">a\r\nMK\r\nTA\r\n>b\r\nGG",            # CRLF, no trailing newline
+    b"",                                       # empty file -> one ("", "") record
+    b"MKT\n>a\nAA\n",                          # sequence lines before the first header stick to it
+    b">a\nAA\n>b\nCC\n>a\nDD\n",               # repeated header: last sequence wins
+    b">\nAA\n>b\nCC\n",                        # empty header does not flush
+    b">a\nAA\n\n\n>b\n\nCC\n",                 # blank lines
+    b">a\nAA\n>bad\xff\xfe\nCC\n>c\nDD\n",     # invalid UTF-8 header line vanishes: CC joins record a
+    b">a\n M K T \n",                          # no trimming
+])
+def test_read_fasta_semantics(hostlib, tmp_path, content):
+    p = tmp_path / "x.fa"
+    p.write_bytes(content)
+    assert _read_fasta_cpp(hostlib, str(p)) == list(H.read_fasta(str(p)).items())
+
+
+def _make_inputs(d):
+    d.mkdir()
+    (d / "Spec_one.fa").write_text(">sp|P1|first protein (x)\nMKTAYIAKQR\nQISFVKSHFS\n>short\nM\n>sp|P2|second;one\nGGGGGGGG\n")
+    (d / "Spec.two.fasta").write_text(">dup of P2\nGGGGGGGG\n>long one\n" + "ACDEFGHIKL" * 30 + "\n")
+    (d / "ignored.txt").write_text(">x\nAAAA\n")
+    (d / ".fa").write_text(">hidden\nCCCC\n")
+    return d
+
+
+def _run(args, **kw):
+    return subprocess.run(args, capture_output=True, text=True, timeout=120, **kw)
+
+
+def test_cli_host_flow_until_device(tmp_path, tiny_dir):
+    inp = _make_inputs(tmp_path / "in")
+    out = tmp_path / "out" / "db" / "proteome_db"
+    p = _run([UNICORE, "createdb", str(inp), str(out), tiny_dir, "--max-len", "200"])
+    import torch
+    if torch.cuda.is_available():
+        assert p.returncode == 0, p.stderr
+    else:
+        assert p.returncode == 1 and "no CPU fallback" in p.stderr  # fails loudly at the device boundary
+        assert (out.parent / "createdb.chk").read_text() == "0"     # never "1" after a failed run
+        assert (out.parent / "combined_aa.fasta").exists()
+    data, lines = H.collect(str(inp), max_len=200)
+    got = [tuple(l.split("\t")) for l in open(str(out) + ".map").read().splitlines()]
+    assert sorted(got) == sorted(lines) and len(got) == 3  # short + long dropped, duplicate keeps two lines
+    assert {g[1] for g in got} == {"Spec_one", "Spec.two"}
+    if not torch.cuda.is_available():
+        comb = H.read_fasta(str(out.parent / "combined_aa.fasta"))
+        assert comb == data and len(comb) == 2
+
+
+def test_cli_argument_and_contract_errors(tmp_path, tiny_dir):
+    inp = _make_inputs(tmp_path / "in")
+    assert _run([UNICORE, "createdb", str(inp)]).returncode == 0x40
+    p = _run([UNICORE, "createdb", str(inp), str(tmp_path / "o" / "db"), tiny_dir, "--afdb-lookup", "a", "--custom-lookup", "b"])
+    assert p.returncode == 0x40 and "Both afdb_lookup and custom_lookup" in p.stderr
+    (tmp_path / "done").mkdir()
+    (tmp_path / "done" / "createdb.chk").write_text("1")
+    p = _run([UNICORE, "createdb", str(inp), str(tmp_path / "done" / "db"), tiny_dir])
+    assert p.returncode == 1 and "Database already exists, skipping createdb module" in p.stderr
+    old = tmp_path / "oldw"
+    old.mkdir()
+    (old / "cnn.safetensors").write_bytes(b"x")
+    p = _run([UNICORE, "createdb", str(inp), str(tmp_path / "o2" / "db"), str(old)])
+    assert p.returncode == 1 and "Old weight files detected" in p.stderr
+    p = _run([UNICORE, "createdb", str(inp), str(tmp_path / "o3" / "db"), str(tmp_path / "noweights")])
+    assert p.returncode == 0x10 and "prostt5-f16.gguf" in p.stderr
+    p = _run([UNICORE, "createdb", str(tmp_path / "missing"), str(tmp_path / "o4" / "db"), tiny_dir])
+    assert p.returncode == 1 and "Input is not a directory or a file" in p.stderr
+    assert _run([UNICORE, "version"]).returncode == 0
+    assert _run([UNICORE, "cluster", "a", "b", "c"]).returncode == 0x30
+
+
+def test_shim_contract(tmp_path):
+    p = _run([SHIM, "version"])  # `unicore config --set-foldseek` runs `<binary> version` [REF src/modules/config.rs:49-60]
+    assert p.returncode == 0 and "foldseek-b200" in p.stdout
+    p = _run([SHIM, "cluster", "db", "out", "tmp"], env={**os.environ, "UNICORE_B200_REAL_FOLDSEEK": ""})
+    assert p.returncode == 1 and "not implemented" in p.stderr
+    fake = tmp_path / "real_foldseek"
+    fake.write_text("#!/bin/sh\necho real \"$@\"\n")
+    fake.chmod(0o755)
+    p = _run([SHIM, "cluster", "db", "out", "tmp"], env={**os.environ, "UNICORE_B200_REAL_FOLDSEEK": str(fake)})
+    assert p.returncode == 0 and p.stdout.strip() == "real cluster db out tmp"
+
+
+def test_example_data_map_matches_golden(tmp_path, tiny_dir):
+    src = "/root/reference/example/data"
+    if not os.path.isdir(src):
+        pytest.skip("reference tree not present (GPU box)")
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "example_data_host.json")))
+    out = tmp_path / "o" / "db"
+    _run([UNICORE, "createdb", src, str(out), tiny_dir, "-v", "0"])
+    lines = sorted(open(str(out) + ".map").read().splitlines(keepends=True))
+    assert len(lines) == gold["map_lines"] == 1276
+    assert hashlib.md5("".join(lines).encode()).hexdigest() == gold["map_sorted_md5"]
+    assert [l.rstrip("\n") for l in lines[:3]] == gold["first_sorted_lines"]

@@ -602,8 +602,13 @@ Model* model_load(const std::string& dir, const int* devices, int n_devices) {
                                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)));
     }
     std::vector<int> devs;
-    if (devices == nullptr || n_devices <= 0) devs.push_back(0);
-    else devs.assign(devices, devices + n_devices);
+    if (n_devices < 0) {  // every visible device (CUDA_VISIBLE_DEVICES selects, as for the reference [REF README.md:142-145])
+        for (int i = 0; i < ndev_avail; ++i) devs.push_back(i);
+    } else if (devices == nullptr || n_devices == 0) {
+        devs.push_back(0);
+    } else {
+        devs.assign(devices, devices + n_devices);
+    }
     for (int dv : devs) P5_REQUIRE(dv >= 0 && dv < ndev_avail, P5_ERR_ARG, "device %d does not exist (%d visible)", dv, ndev_avail);
     m->devs.resize(devs.size());
     // replicate the weights: one loader thread per device (each reads the shared mmap)
