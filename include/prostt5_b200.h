@@ -69,6 +69,7 @@ int p5_bias_table(const p5_model* m, uint32_t head, float* out);
  *                       ProstT5 script applied to a batch of one; 0: zero padding starts right after the
  *                       last residue
  *   "gemm_variant"      1 (default) CTA-pair tcgen05 GEMM, 0 single-CTA
+ *   "attn_impl"         1 (default) tcgen05 attention kernel, 0 legacy mma.sync kernel
  *   "profile"           1: time every kernel class with CUDA events on the launch stream (p5_get_stats) */
 int p5_set_option(p5_model* m, const char* key, int64_t value);
 

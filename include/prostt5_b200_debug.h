@@ -32,10 +32,11 @@ int p5_dbg_gemm_bench(int device, int variant, int epilogue, uint32_t M, uint32_
                       float* ms_out);
 
 /* Relative-position-bias attention over packed sequences, in isolation.
+ * impl: 1 = tcgen05 kernel (attention_tc.cu, the product default), 0 = mma.sync kernel (attention.cu).
  * qkv_host [M, 3*n_head*128] fp16 (Q | K | V), cu_host [n_seq+1] token offsets (M = cu_host[n_seq]),
  * bias_host [n_head, 2*max_dist+1] fp32 (natural-log domain, indexed by clamp(key-query)+max_dist),
  * ctx_host [M, n_head*128] fp16 out.  iters>0: mean ms per launch over `iters` launches in *ms_out. */
-int p5_dbg_attention(int device, const uint16_t* qkv_host, const int32_t* cu_host, uint32_t n_seq, uint32_t n_head,
+int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, const int32_t* cu_host, uint32_t n_seq, uint32_t n_head,
                      uint32_t max_dist, const float* bias_host, uint16_t* ctx_host, int iters, float* ms_out);
 
 /* Thread-local message of the last failed call on this thread (also declared in prostt5_b200.h). */

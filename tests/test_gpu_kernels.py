@@ -73,9 +73,10 @@ def _attention_ref(qkv, cu, H, bias, md):
     return out
 
 
+@pytest.mark.parametrize("impl", [1, 0])
 @pytest.mark.parametrize("lens,H", [([1], 1), ([3], 1), ([64], 2), ([65, 1, 130], 2), ([352, 352], 4),
-                                    ([700, 66, 1026], 2), ([2500], 1)])
-def test_attention_matches_numpy(lens, H):
+                                    ([700, 66, 1026], 2), ([2500], 1), ([128, 129, 127, 256, 257], 3)])
+def test_attention_matches_numpy(lens, H, impl):
     lib = _lib.load()
     rng = np.random.default_rng(sum(lens) + H)
     cu = np.zeros(len(lens) + 1, np.int32)
@@ -85,14 +86,15 @@ def test_attention_matches_numpy(lens, H):
     bias = (rng.standard_normal((H, 2 * md + 1), dtype=np.float32) * 0.5).astype(np.float32)
     ctx = np.zeros((M, H * 128), np.float16)
     ms = C.c_float(0)
-    _lib.check(lib.p5_dbg_attention(0, qkv.ctypes.data, cu.ctypes.data, len(lens), H, md, bias.ctypes.data,
+    _lib.check(lib.p5_dbg_attention(0, impl, qkv.ctypes.data, cu.ctypes.data, len(lens), H, md, bias.ctypes.data,
                                     ctx.ctypes.data, 0, C.byref(ms)))
     ref = _attention_ref(qkv, cu, H, bias, md)
     # tolerance: ctx is stored fp16 (2^-11 relative) + fp16 rounding of P against a different running max
     assert np.abs(ctx.astype(np.float32) - ref).max() < 4e-3
 
 
-def test_attention_peaked_scores():
+@pytest.mark.parametrize("impl", [1, 0])
+def test_attention_peaked_scores(impl):
     """Un-scaled T5 scores can be large: one dominant key per row must not overflow or lose the row."""
     lib = _lib.load()
     rng = np.random.default_rng(3)
@@ -102,8 +104,8 @@ def test_attention_peaked_scores():
     bias = np.zeros((H, 2 * md + 1), np.float32)
     ctx = np.zeros((T, 128), np.float16)
     ms = C.c_float(0)
-    _lib.check(lib.p5_dbg_attention(0, qkv.ctypes.data, cu.ctypes.data, 1, H, md, bias.ctypes.data, ctx.ctypes.data, 0,
-                                    C.byref(ms)))
+    _lib.check(lib.p5_dbg_attention(0, impl, qkv.ctypes.data, cu.ctypes.data, 1, H, md, bias.ctypes.data,
+                                    ctx.ctypes.data, 0, C.byref(ms)))
     ref = _attention_ref(qkv, cu, H, bias, md)
     assert np.isfinite(ctx.astype(np.float32)).all()
     assert np.abs(ctx.astype(np.float32) - ref).max() < 2e-2

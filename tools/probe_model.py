@@ -36,7 +36,7 @@ def attn_ref(qkv, cu, H, bias, md):
     return out
 
 
-def stage_attn():
+def stage_attn(impl=1):
     import ctypes as C
     from unicore_b200 import _lib
     lib = _lib.load()
@@ -51,14 +51,14 @@ def stage_attn():
         bias = (rng.standard_normal((H, 2 * md + 1), dtype=np.float32) * 0.5).astype(np.float32)
         ctx = np.zeros((M, H * 128), np.float16)
         ms = C.c_float(0)
-        rc = lib.p5_dbg_attention(0, qkv.ctypes.data, cu.ctypes.data, len(lens), H, md, bias.ctypes.data, ctx.ctypes.data,
+        rc = lib.p5_dbg_attention(0, impl, qkv.ctypes.data, cu.ctypes.data, len(lens), H, md, bias.ctypes.data, ctx.ctypes.data,
                                   0, C.byref(ms))
         if rc:
             res.append({"lens": lens, "error": lib.p5_last_error().decode()})
             continue
         ref = attn_ref(qkv, cu, H, bias, md)
         err = np.abs(ctx.astype(np.float32) - ref)
-        res.append({"lens": lens, "H": H, "max_err": float(err.max()), "ref_absmax": float(np.abs(ref).max()),
+        res.append({"impl": impl, "lens": lens, "H": H, "max_err": float(err.max()), "ref_absmax": float(np.abs(ref).max()),
                     "ok": bool(err.max() < 5e-3)})
     # timing at config-2 shape: 256 seqs x 352 tokens, 32 heads
     lens = [352] * 256
@@ -71,7 +71,7 @@ def stage_attn():
     bias = np.zeros((H, 257), np.float32)
     ctx = np.zeros((M, H * 128), np.float16)
     ms = C.c_float(0)
-    rc = lib.p5_dbg_attention(0, qkv.ctypes.data, cu.ctypes.data, len(lens), H, 128, bias.ctypes.data, ctx.ctypes.data, 10,
+    rc = lib.p5_dbg_attention(0, impl, qkv.ctypes.data, cu.ctypes.data, len(lens), H, 128, bias.ctypes.data, ctx.ctypes.data, 10,
                               C.byref(ms))
     fl = 4.0 * H * 128 * sum(t * t for t in lens)
     res.append({"bench": "256x352x32h", "ms": ms.value, "tflops": fl / (ms.value * 1e-3) / 1e12 if ms.value else None,
@@ -172,7 +172,7 @@ def stage_bench():
     return res
 
 
-STAGES = {"attn": stage_attn, "tiny": stage_tiny, "full": stage_full, "bench": stage_bench}
+STAGES = {"attn": stage_attn, "attn0": lambda: stage_attn(0), "tiny": stage_tiny, "full": stage_full, "bench": stage_bench}
 
 
 def main():

@@ -20,12 +20,12 @@ thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 const char* last_error_cstr() { return g_last_error.c_str(); }
 
-struct DevBuf {
+struct ScratchBuf {
     void* p = nullptr;
-    explicit DevBuf(size_t bytes) { P5_CUDA(cudaMalloc(&p, bytes ? bytes : 1)); }
-    ~DevBuf() { cudaFree(p); }
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
+    explicit ScratchBuf(size_t bytes) { P5_CUDA(cudaMalloc(&p, bytes ? bytes : 1)); }
+    ~ScratchBuf() { cudaFree(p); }
+    ScratchBuf(const ScratchBuf&) = delete;
+    ScratchBuf& operator=(const ScratchBuf&) = delete;
 };
 
 }  // namespace p5
@@ -46,7 +46,7 @@ extern "C" int p5_dbg_gemm(int device, int variant, int epilogue, uint32_t M, ui
         const Epi epi = static_cast<Epi>(epilogue);
         const bool f16_out = (epi == Epi::StoreF16 || epi == Epi::StoreF16Relu);
         const size_t c_bytes = size_t(M) * N * (f16_out ? 2 : 4);
-        DevBuf a(size_t(M) * K * 2), b(size_t(N) * K * 2), c(c_bytes);
+        ScratchBuf a(size_t(M) * K * 2), b(size_t(N) * K * 2), c(c_bytes);
         P5_CUDA(cudaMemcpy(a.p, a_host, size_t(M) * K * 2, cudaMemcpyHostToDevice));
         P5_CUDA(cudaMemcpy(b.p, b_host, size_t(N) * K * 2, cudaMemcpyHostToDevice));
         P5_CUDA(cudaMemcpy(c.p, c_host, c_bytes, cudaMemcpyHostToDevice));
@@ -104,7 +104,7 @@ extern "C" int p5_dbg_gemm_bench(int device, int variant, int epilogue, uint32_t
         const Epi epi = static_cast<Epi>(epilogue);
         const bool f16_out = (epi == Epi::StoreF16 || epi == Epi::StoreF16Relu);
         const size_t c_bytes = size_t(M) * N * (f16_out ? 2 : 4);
-        DevBuf a(size_t(M) * K * 2), b(size_t(N) * K * 2), c(c_bytes);
+        ScratchBuf a(size_t(M) * K * 2), b(size_t(N) * K * 2), c(c_bytes);
         cudaStream_t st;
         P5_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         fill_random_f16<<<1184, 256, 0, st>>>(static_cast<__half*>(a.p), size_t(M) * K, 1u);
@@ -129,24 +129,36 @@ extern "C" int p5_dbg_gemm_bench(int device, int variant, int epilogue, uint32_t
     });
 }
 
-extern "C" int p5_dbg_attention(int device, const uint16_t* qkv_host, const int32_t* cu_host, uint32_t n_seq,
+extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, const int32_t* cu_host, uint32_t n_seq,
                                 uint32_t n_head, uint32_t max_dist, const float* bias_host, uint16_t* ctx_host, int iters,
                                 float* ms_out) {
     return guarded([&] {
         P5_REQUIRE(qkv_host && cu_host && bias_host && ctx_host && n_seq >= 1, P5_ERR_ARG, "null buffer");
         P5_CUDA(cudaSetDevice(device));
         attention_init_device();
+        attention_tc_init_device();
+        P5_REQUIRE(impl == 0 || impl == 1, P5_ERR_ARG, "impl must be 0 (mma.sync) or 1 (tcgen05)");
+        cudaDeviceProp prop;
+        P5_CUDA(cudaGetDeviceProperties(&prop, device));
         const uint32_t M = uint32_t(cu_host[n_seq]);
         const size_t inner = size_t(n_head) * kHeadDim;
         std::vector<int2> work;
         for (uint32_t s = 0; s < n_seq; ++s) {
             const int T = cu_host[s + 1] - cu_host[s];
             P5_REQUIRE(T >= 1, P5_ERR_ARG, "empty sequence %u", s);
-            for (int q = 0; q < T; q += int(kAttnBlockM)) work.push_back(make_int2(int(s), q));
+            for (int q = 0; q < T; q += int(impl ? kAttnTcBlockM : kAttnBlockM)) work.push_back(make_int2(int(s), q));
         }
-        DevBuf qkv(M * 3 * inner * 2), ctx(M * inner * 2), cu((n_seq + 1) * 4), wk(work.size() * sizeof(int2)),
+        const size_t Mpad = (size_t(M) + 255) / 256 * 256;  // TMA boxes may reach past the last sequence: zero rows
+        std::vector<float> e_host(size_t(n_head) * kAttnTcTable);
+        attention_tc_build_table(bias_host, n_head, max_dist, e_host.data());
+        ScratchBuf e_ext(e_host.size() * 4);
+        P5_CUDA(cudaMemcpy(e_ext.p, e_host.data(), e_host.size() * 4, cudaMemcpyHostToDevice));
+        ScratchBuf qkv(Mpad * 3 * inner * 2), ctx(M * inner * 2), cu((n_seq + 1) * 4), wk(work.size() * sizeof(int2)),
             bias(size_t(n_head) * (2 * max_dist + 1) * 4);
+        P5_CUDA(cudaMemset(qkv.p, 0, Mpad * 3 * inner * 2));
         P5_CUDA(cudaMemcpy(qkv.p, qkv_host, M * 3 * inner * 2, cudaMemcpyHostToDevice));
+        CUtensorMap tm_q = make_kmajor_tensor_map(qkv.p, Mpad, 3 * inner, 3 * inner, kAttnTcBlockM);
+        CUtensorMap tm_kv = make_kmajor_tensor_map(qkv.p, Mpad, 3 * inner, 3 * inner, 64);
         P5_CUDA(cudaMemcpy(cu.p, cu_host, (n_seq + 1) * 4, cudaMemcpyHostToDevice));
         P5_CUDA(cudaMemcpy(wk.p, work.data(), work.size() * sizeof(int2), cudaMemcpyHostToDevice));
         P5_CUDA(cudaMemcpy(bias.p, bias_host, size_t(n_head) * (2 * max_dist + 1) * 4, cudaMemcpyHostToDevice));
@@ -154,6 +166,12 @@ extern "C" int p5_dbg_attention(int device, const uint16_t* qkv_host, const int3
         cudaStream_t st;
         P5_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         auto run = [&] {
+            if (impl == 1) {
+                launch_attention_tc(st, prop.multiProcessorCount, tm_q, tm_kv, static_cast<__half*>(ctx.p),
+                                    static_cast<const int32_t*>(cu.p), static_cast<const int2*>(wk.p),
+                                    uint32_t(work.size()), static_cast<const float*>(e_ext.p), n_head, max_dist);
+                return;
+            }
             launch_attention(st, static_cast<const __half*>(qkv.p), static_cast<__half*>(ctx.p),
                              static_cast<const int32_t*>(cu.p), static_cast<const int2*>(wk.p), uint32_t(work.size()),
                              static_cast<const float*>(bias.p), n_head, max_dist);

@@ -1,0 +1,349 @@
+// Relative-position-bias self-attention on the 5th-generation tensor cores (SURVEY.md §8a p5,p6):
+//   ctx[i, h] = softmax_j( Q[i,h].K[j,h] + bias[h][bucket(j-i)] ) . V[j,h]      (no 1/sqrt(d) scale)
+//
+// Persistent kernel, two CTAs per SM (256 of the 512 TMEM columns each), 192 threads per CTA:
+//   warps 0-3  softmax: thread r owns query row r of the 128-row tile (TMEM lane r): tcgen05.ld of
+//              S, bias + mask + running max in the log2 domain, exp2, fp16 P written BACK INTO TMEM over
+//              the S columns (tcgen05.st), lazy rescale of the O accumulator, final O/l -> global
+//   warp 4     TMA producer: Q (128 x 128), then K and V in 64-key tiles through two 2-stage rings
+//   warp 5     MMA issuer (one thread): S = Q.K^T (UMMA 128x64x16, both operands from 128B-swizzled
+//              smem) and O += P.V (UMMA 128x128x16, A = P from TMEM, B = V MN-major from smem)
+// The S for tile j+1 is issued before P.V of tile j, so the tensor pipe works on the next scores while
+// the softmax warps are busy; the second resident CTA fills the remaining bubbles.
+// Work item = (sequence, 128-query tile, head); items are dealt round-robin to the persistent CTAs.
+#include "kernels.h"
+
+#include "common.h"
+#include "gemm_launch.h"
+#include "ptx.cuh"
+
+namespace p5 {
+
+namespace {
+
+constexpr uint32_t kBM = kAttnTcBlockM, kBN = 64, kD = kHeadDim;
+constexpr uint32_t kThreads = 192;
+constexpr uint32_t kQBytes = kBM * kD * 2;   // 32 KB: two 128-row x 64-col boxes
+constexpr uint32_t kKVBytes = kBN * kD * 2;  // 16 KB: two 64-row x 64-col boxes
+constexpr uint32_t kEHalf = 320, kEPad = 644;  // extended bias table: offsets -320..+320 (641 entries)
+constexpr uint32_t kSmemQ = 0;
+constexpr uint32_t kSmemK = kSmemQ + kQBytes;
+constexpr uint32_t kSmemV = kSmemK + 2 * kKVBytes;
+constexpr uint32_t kSmemE = kSmemV + 2 * kKVBytes;
+constexpr uint32_t kSmemBar = kSmemE + 2 * kEPad * 4;
+constexpr uint32_t kNumBars = 18;
+constexpr uint32_t kSmemTotal = kSmemBar + kNumBars * 8 + 16;
+constexpr uint32_t kSmemDynamic = kSmemTotal + 1024;  // slack for manual 1024 B alignment
+constexpr uint32_t kTmemCols = 256;                   // O: [0,128)  S/P buffer 0: [128,192)  buffer 1: [192,256)
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays below 2^8 between rescales
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct Item {
+    int tok0, T, q0, h;
+    uint32_t nt;
+};
+__device__ __forceinline__ Item get_item(uint32_t item, uint32_t H, const int2* __restrict__ work,
+                                         const int32_t* __restrict__ cu) {
+    const uint32_t w = item / H;
+    const int2 wk = work[w];
+    Item it;
+    it.h = int(item - w * H);
+    it.tok0 = cu[wk.x];
+    it.T = cu[wk.x + 1] - it.tok0;
+    it.q0 = wk.y;
+    it.nt = uint32_t(it.T + int(kBN) - 1) / kBN;
+    return it;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                    __half* __restrict__ ctx, const int32_t* __restrict__ cu, const int2* __restrict__ work,
+                    uint32_t n_items, uint32_t H, const float* __restrict__ e_ext) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
+    uint64_t* q_full = bars + 0;
+    uint64_t* q_empty = bars + 1;
+    uint64_t* k_full = bars + 2;   // [2]
+    uint64_t* k_empty = bars + 4;  // [2]
+    uint64_t* v_full = bars + 6;   // [2]
+    uint64_t* v_empty = bars + 8;  // [2]
+    uint64_t* s_full = bars + 10;  // [2]
+    uint64_t* p_full = bars + 12;  // [2]
+    uint64_t* pv_done = bars + 14;  // [2]: P.V of even / odd tiles.  A waiter may lag ONE phase behind an mbarrier,
+                                    // never two; with one barrier per tile parity the previous completion of
+                                    // the same barrier (tile g-2) is always known to be complete (S_g was seen)
+    uint64_t* o_empty = bars + 16;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + kNumBars);
+    float* e_smem = reinterpret_cast<float*>(smem + kSmemE);
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = ptx::lane_id();
+
+    if (warp == 5 && lane == 0) {
+        ptx::mbar_init(q_full, 1);
+        ptx::mbar_init(q_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&k_full[i], 1);
+            ptx::mbar_init(&k_empty[i], 1);
+            ptx::mbar_init(&v_full[i], 1);
+            ptx::mbar_init(&v_empty[i], 1);
+            ptx::mbar_init(&s_full[i], 1);
+            ptx::mbar_init(&p_full[i], 4);  // one arrive per softmax warp
+        }
+        ptx::mbar_init(&pv_done[0], 1);
+        ptx::mbar_init(&pv_done[1], 1);
+        ptx::mbar_init(o_empty, 4);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 4) {
+        if (lane == 0) {
+            ptx::prefetch_tensormap(&tm_q);
+            ptx::prefetch_tensormap(&tm_kv);
+        }
+        ptx::tmem_alloc<1>(tmem_ptr_smem, kTmemCols);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
+    const uint32_t sQ = ptx::smem_u32(smem + kSmemQ);
+    const uint32_t sK = ptx::smem_u32(smem + kSmemK);
+    const uint32_t sV = ptx::smem_u32(smem + kSmemV);
+
+    if (warp == 4) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            uint32_t g = 0, n = 0;
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+                const Item it = get_item(item, H, work, cu);
+                const int32_t qcol = it.h * int(kD);
+                const int32_t kcol = int(H * kD) + qcol;
+                const int32_t vcol = 2 * int(H * kD) + qcol;
+                if (n > 0) ptx::mbar_wait(q_empty, (n - 1) & 1);  // every S of the previous item has read Q
+                ptx::mbar_arrive_expect_tx(q_full, kQBytes);
+                ptx::tma_load_2d(&tm_q, q_full, smem + kSmemQ, qcol, it.tok0 + it.q0, ptx::kEvictNormal);
+                ptx::tma_load_2d(&tm_q, q_full, smem + kSmemQ + kQBytes / 2, qcol + 64, it.tok0 + it.q0, ptx::kEvictNormal);
+                for (uint32_t j = 0; j < it.nt; ++j, ++g) {
+                    const uint32_t st = g & 1, ph = (g >> 1) & 1;
+                    const int32_t row = it.tok0 + int(j * kBN);
+                    uint8_t* dk = smem + kSmemK + st * kKVBytes;
+                    uint8_t* dv = smem + kSmemV + st * kKVBytes;
+                    ptx::mbar_wait(&k_empty[st], ph ^ 1);
+                    ptx::mbar_arrive_expect_tx(&k_full[st], kKVBytes);
+                    ptx::tma_load_2d(&tm_kv, &k_full[st], dk, kcol, row, ptx::kEvictNormal);
+                    ptx::tma_load_2d(&tm_kv, &k_full[st], dk + kKVBytes / 2, kcol + 64, row, ptx::kEvictNormal);
+                    ptx::mbar_wait(&v_empty[st], ph ^ 1);
+                    ptx::mbar_arrive_expect_tx(&v_full[st], kKVBytes);
+                    ptx::tma_load_2d(&tm_kv, &v_full[st], dv, vcol, row, ptx::kEvictNormal);
+                    ptx::tma_load_2d(&tm_kv, &v_full[st], dv + kKVBytes / 2, vcol + 64, row, ptx::kEvictNormal);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = ptx::make_idesc_f16_f32(kBM, kBN);
+            constexpr uint32_t idesc_pv = ptx::make_idesc_f16_f32(kBM, kD) | ptx::kIdescBMnMajor;
+            uint32_t g = 0, n = 0;
+            // O += P_gg . V_gg   (gg = global tile index, jj = index inside the item)
+            auto issue_pv = [&](uint32_t gg, uint32_t jj) {
+                const uint32_t st = gg & 1, ph = (gg >> 1) & 1;
+                ptx::mbar_wait(&v_full[st], ph);
+                ptx::mbar_wait(&p_full[st], ph);
+                if (jj == 0 && n > 0) ptx::mbar_wait(o_empty, (n - 1) & 1);  // previous item's O has been read out
+                ptx::tc_fence_after();
+                const uint32_t a_tmem = tmem_base + 128 + st * kBN;
+#pragma unroll
+                for (uint32_t ks = 0; ks < kBN / 16; ++ks) {
+                    // 16 keys per step = two 8-row groups of the MN-major V tile (2 x 1024 B)
+                    const uint64_t b = ptx::make_mnmajor_sw128_desc(sV + st * kKVBytes + ks * 2048, kKVBytes / 2, 1024);
+                    ptx::umma_f16_ts(tmem_base, a_tmem + ks * 8, b, idesc_pv, (jj | ks) != 0u);
+                }
+                ptx::umma_commit<1>(&v_empty[st]);
+                ptx::umma_commit<1>(&pv_done[st]);
+            };
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+                const Item it = get_item(item, H, work, cu);
+                ptx::mbar_wait(q_full, n & 1);
+                ptx::tc_fence_after();
+                for (uint32_t j = 0; j < it.nt; ++j, ++g) {
+                    const uint32_t st = g & 1, ph = (g >> 1) & 1;
+                    ptx::mbar_wait(&k_full[st], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + 128 + st * kBN;
+#pragma unroll
+                    for (uint32_t ks = 0; ks < kD / 16; ++ks) {
+                        const uint32_t half = ks >> 2, kk = ks & 3;
+                        const uint64_t a = ptx::make_kmajor_sw128_desc(sQ + half * (kQBytes / 2)) + kk * 2;
+                        const uint64_t b = ptx::make_kmajor_sw128_desc(sK + st * kKVBytes + half * (kKVBytes / 2)) + kk * 2;
+                        ptx::umma_f16<1>(d_tmem, a, b, idesc_s, ks != 0u);
+                    }
+                    ptx::umma_commit<1>(&k_empty[st]);
+                    ptx::umma_commit<1>(&s_full[st]);
+                    if (j + 1 == it.nt) ptx::umma_commit<1>(q_empty);
+                    if (j >= 1) issue_pv(g - 1, j - 1);
+                }
+                issue_pv(g - 1, it.nt - 1);
+            }
+        }
+    } else {
+        // =============================== softmax warps ===============================
+        const uint32_t r = warp * 32 + lane;  // row of the tile == TMEM lane
+        const uint32_t t_lane = tmem_base + ((warp * 32u) << 16);
+        uint32_t g = 0, n = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+            const Item it = get_item(item, H, work, cu);
+            float* es = e_smem + (n & 1) * kEPad;
+            for (uint32_t i = threadIdx.x; i < 2 * kEHalf + 1; i += 128) es[i] = e_ext[size_t(it.h) * kEPad + i];
+            ptx::named_bar_sync(1, 128);
+            const int row_seq = it.q0 + int(r);
+            const float e_lo = es[0], e_hi = es[2 * kEHalf];
+            float m = -INFINITY, l = 0.f;
+            for (uint32_t j = 0; j < it.nt; ++j, ++g) {
+                const uint32_t b = g & 1, ph = (g >> 1) & 1;
+                const int j0 = int(j * kBN);
+                ptx::mbar_wait(&s_full[b], ph);
+                ptx::tc_fence_after();
+                uint32_t v0[32], v1[32];
+                ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN, v0);
+                ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN + 32, v1);
+                ptx::tmem_ld_wait();
+                float z[64];
+                // bias: constant when the whole tile is beyond +-128 of the diagonal, table otherwise
+                const int dmin = j0 - (it.q0 + int(kBM) - 1), dmax = j0 + int(kBN) - 1 - it.q0;
+                if (dmax <= -128 || dmin >= 128) {
+                    const float e = dmax <= -128 ? e_lo : e_hi;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        z[c] = fmaf(__uint_as_float(v0[c]), kLog2e, e);
+                        z[32 + c] = fmaf(__uint_as_float(v1[c]), kLog2e, e);
+                    }
+                } else {
+                    const float* er = es + (int(kEHalf) - row_seq + j0);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        z[c] = fmaf(__uint_as_float(v0[c]), kLog2e, er[c]);
+                        z[32 + c] = fmaf(__uint_as_float(v1[c]), kLog2e, er[32 + c]);
+                    }
+                }
+                if (j0 + int(kBN) > it.T) {
+#pragma unroll
+                    for (int c = 0; c < 64; ++c)
+                        if (j0 + c >= it.T) z[c] = -INFINITY;
+                }
+                float mx = z[0];
+#pragma unroll
+                for (int c = 1; c < 64; ++c) mx = fmaxf(mx, z[c]);
+                if (j == 0) {
+                    m = mx;  // key 0 is always valid, so mx is finite
+                } else if (__any_sync(0xffffffffu, mx > m + kRescaleThreshold)) {
+                    // rescale the O accumulator of this warp's 32 rows (rare after the first tiles)
+                    const float m_new = fmaxf(m, mx);
+                    const float alpha = ex2(m - m_new);
+                    m = m_new;
+                    l *= alpha;
+                    ptx::mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);  // P.V of the previous tile has landed in O
+                    ptx::tc_fence_after();
+#pragma unroll 1
+                    for (uint32_t c = 0; c < kD / 32; ++c) {
+                        uint32_t o[32];
+                        ptx::tmem_ld_32x32b_x32(t_lane + c * 32, o);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        ptx::tmem_st_32x32b_x32(t_lane + c * 32, o);
+                    }
+                    ptx::tmem_st_wait();
+                }
+                uint32_t pk[32];
+                float sum = 0.f;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float p0 = ex2(z[2 * c] - m), p1 = ex2(z[2 * c + 1] - m);
+                    sum += p0 + p1;
+                    pk[c] = pack_h2(p0, p1);
+                }
+                l += sum;
+                ptx::tmem_st_32x32b_x32(t_lane + 128 + b * kBN, pk);  // P over the first 32 columns of S
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&p_full[b]);
+            }
+            // ---- epilogue: O / l -> ctx ----
+            // the last two P.V (one per barrier) may both still be in flight: wait for both, older first
+            if (it.nt >= 2) ptx::mbar_wait(&pv_done[(g - 2) & 1], ((g - 2) >> 1) & 1);
+            ptx::mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
+            ptx::tc_fence_after();
+            const float inv = 1.f / l;
+            __half* dst = ctx + size_t(it.tok0 + row_seq) * (size_t(H) * kD) + size_t(it.h) * kD;
+#pragma unroll 1
+            for (uint32_t c = 0; c < kD / 32; ++c) {
+                uint32_t o[32];
+                ptx::tmem_ld_32x32b_x32(t_lane + c * 32, o);
+                ptx::tmem_ld_wait();
+                if (row_seq < it.T) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 u;
+                        u.x = pack_h2(__uint_as_float(o[8 * q + 0]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
+                        u.y = pack_h2(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
+                        u.z = pack_h2(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
+                        u.w = pack_h2(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
+                        *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = u;
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(o_empty);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) ptx::tmem_dealloc<1>(tmem_base, kTmemCols);
+}
+
+}  // namespace
+
+void attention_tc_init_device() {
+
+    P5_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemDynamic)));
+}
+
+// extended, log2-domain bias table of one model: e_ext[h][kAttnTcTable] with
+// e_ext[h][i] = log2(e) * bias[h][clamp(i - 320, -max_dist, +max_dist) + max_dist]
+void attention_tc_build_table(const float* bias, uint32_t H, uint32_t max_dist, float* e_ext) {
+    for (uint32_t h = 0; h < H; ++h)
+        for (uint32_t i = 0; i < kEPad; ++i) {
+            int d = int(i) - int(kEHalf);
+            d = d < -int(max_dist) ? -int(max_dist) : (d > int(max_dist) ? int(max_dist) : d);
+            e_ext[size_t(h) * kEPad + i] = bias[size_t(h) * (2 * max_dist + 1) + size_t(d + int(max_dist))] * kLog2e;
+        }
+}
+
+void launch_attention_tc(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, const CUtensorMap& tm_kv, __half* ctx,
+                         const int32_t* cu, const int2* work128, uint32_t n_work, const float* e_ext, uint32_t H,
+                         uint32_t max_dist) {
+    if (n_work == 0) return;
+    P5_REQUIRE(max_dist <= 128, P5_ERR_UNSUPPORTED,
+               "relative attention max distance %u: the tcgen05 attention kernel assumes <= 128", max_dist);
+    const uint64_t n_items = uint64_t(n_work) * H;
+    P5_REQUIRE(n_items < (1ull << 31), P5_ERR_UNSUPPORTED, "too many attention work items");
+    const uint32_t grid = uint32_t(std::min<uint64_t>(n_items, uint64_t(2 * num_sms)));
+    attention_tc_kernel<<<grid, kThreads, kSmemDynamic, st>>>(tm_q, tm_kv, ctx, cu, work128, uint32_t(n_items), H, e_ext);
+    P5_CUDA(cudaGetLastError());
+}
+
+}  // namespace p5

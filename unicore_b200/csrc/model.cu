@@ -80,19 +80,21 @@ double unit_flops(const Hyper& hp, uint32_t len) {  // SURVEY.md §8d F_seq(L)
 static void finish_layout(Batch& b) {
     MetaLayout& l = b.lay;
     l.S = uint32_t(b.units.size());
-    l.M = 0; l.n_res = 0; l.n_aw = 0; l.n_hw = 0;
+    l.M = 0; l.n_res = 0; l.n_aw = 0; l.n_aw128 = 0; l.n_hw = 0;
     for (const Unit& u : b.units) {
         const uint32_t T = u.len + 2;
         l.M += T;
         l.n_res += u.len;
         l.n_aw += (T + kAttnBlockM - 1) / kAttnBlockM;
+        l.n_aw128 += (T + kAttnTcBlockM - 1) / kAttnTcBlockM;
         l.n_hw += (u.len + kHeadChunk - 1) / kHeadChunk;
     }
     auto align4 = [](uint32_t w) { return (w + 3u) & ~3u; };  // 16-byte aligned sub-blocks
     l.off_ids = 0;
     l.off_cu = align4(l.M);
     l.off_aw = l.off_cu + align4(l.S + 1);
-    l.off_hw = l.off_aw + align4(2 * l.n_aw);
+    l.off_aw128 = l.off_aw + align4(2 * l.n_aw);
+    l.off_hw = l.off_aw128 + align4(2 * l.n_aw128);
     l.words = l.off_hw + align4(2 * l.n_hw);
 }
 
@@ -145,8 +147,9 @@ static void build_meta(const Model& m, const Batch& b, const uint8_t* aa, int32_
     int32_t* ids = w + l.off_ids;
     int32_t* cu = w + l.off_cu;
     int32_t* aw = w + l.off_aw;
+    int32_t* aw2 = w + l.off_aw128;
     int32_t* hw = w + l.off_hw;
-    uint32_t tok = 0, na = 0, nh = 0;
+    uint32_t tok = 0, na = 0, na2 = 0, nh = 0;
     for (uint32_t s = 0; s < l.S; ++s) {
         const Unit& u = b.units[s];
         cu[s] = int32_t(tok);
@@ -156,6 +159,7 @@ static void build_meta(const Model& m, const Batch& b, const uint8_t* aa, int32_
         ids[tok++] = m.hp.eos_id;
         const uint32_t T = u.len + 2;
         for (uint32_t q = 0; q < T; q += kAttnBlockM) { aw[2 * na] = int32_t(s); aw[2 * na + 1] = int32_t(q); ++na; }
+        for (uint32_t q = 0; q < T; q += kAttnTcBlockM) { aw2[2 * na2] = int32_t(s); aw2[2 * na2 + 1] = int32_t(q); ++na2; }
         for (uint32_t r = 0; r < u.len; r += kHeadChunk) { hw[2 * nh] = int32_t(s); hw[2 * nh + 1] = int32_t(r); ++nh; }
     }
     cu[l.S] = int32_t(tok);
@@ -197,12 +201,12 @@ public:
     float* out_norm = nullptr;
     __half* wc0 = nullptr;  // [K*C1, d] tap-major conv0 weight
     CUtensorMap tm_c0;
-    float *b0 = nullptr, *w1 = nullptr, *b1 = nullptr, *bias = nullptr;
+    float *b0 = nullptr, *w1 = nullptr, *b1 = nullptr, *bias = nullptr, *e_ext = nullptr;
 
     // workspace for `cap` tokens
     uint32_t cap = 0;
     DevBuf h, xn, qkv, ctx, ffn, taps;
-    CUtensorMap tm_xn, tm_ctx, tm_ffn;
+    CUtensorMap tm_xn, tm_ctx, tm_ffn, tm_q, tm_kv;
 
     Slot slots[2];
     std::deque<DevBuf> staged_meta;   // one per staged batch on this device
@@ -313,6 +317,7 @@ void DeviceCtx::init(int device, const Model* m, const GgufFile& g) {
     for (auto& s : slots) P5_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     gemm_init_device();
     attention_init_device();
+    attention_tc_init_device();
 
     const uint32_t d = hp.d_model, inner = hp.d_inner(), ff = hp.d_ff;
     {
@@ -380,6 +385,11 @@ void DeviceCtx::init(int device, const Model* m, const GgufFile& g) {
         b1 = upload<float>(vb1.data(), vb1.size() * 4);
     }
     bias = upload<float>(m->bias_table.data(), m->bias_table.size() * 4);
+    if (hp.max_distance <= 128) {
+        std::vector<float> e(size_t(hp.n_head) * kAttnTcTable);
+        attention_tc_build_table(m->bias_table.data(), hp.n_head, hp.max_distance, e.data());
+        e_ext = upload<float>(e.data(), e.size() * 4);
+    }
     build_weight_maps();
 }
 
@@ -411,12 +421,15 @@ void DeviceCtx::ensure_workspace(uint32_t tokens) {
     ffn.alloc(n * ff * 2);
     taps.alloc(n * size_t(hp.cnn_kernel) * hp.cnn_hidden * 4);
     // rows beyond a batch's M hold stale data: they only feed output rows that are never stored
+    P5_CUDA(cudaMemsetAsync(qkv.p, 0, qkv.bytes, stream));  // attention tiles read (masked) K/V rows past a sequence's end
     P5_CUDA(cudaMemsetAsync(xn.p, 0, xn.bytes, stream));
     P5_CUDA(cudaMemsetAsync(ctx.p, 0, ctx.bytes, stream));
     P5_CUDA(cudaMemsetAsync(ffn.p, 0, ffn.bytes, stream));
     tm_xn = make_kmajor_tensor_map(xn.p, n, d, d, kGemmBlockM);
     tm_ctx = make_kmajor_tensor_map(ctx.p, n, inner, inner, kGemmBlockM);
     tm_ffn = make_kmajor_tensor_map(ffn.p, n, ff, ff, kGemmBlockM);
+    tm_q = make_kmajor_tensor_map(qkv.p, n, 3 * inner, 3 * inner, kAttnTcBlockM);
+    tm_kv = make_kmajor_tensor_map(qkv.p, n, 3 * inner, 3 * inner, 64);
     cap = n;
 }
 
@@ -455,6 +468,7 @@ void DeviceCtx::forward(const MetaLayout& l, const int32_t* meta_d, uint8_t* let
     const int32_t* ids = meta_d + l.off_ids;
     const int32_t* cu = meta_d + l.off_cu;
     const int2* aw = reinterpret_cast<const int2*>(meta_d + l.off_aw);
+    const int2* aw128 = reinterpret_cast<const int2*>(meta_d + l.off_aw128);
     const int2* hw = reinterpret_cast<const int2*>(meta_d + l.off_hw);
     auto gemm = [&](Epi epi, const CUtensorMap& ta, const CUtensorMap& tb, void* C, uint32_t N, uint32_t K) {
         prof_begin(PC_GEMM);
@@ -470,7 +484,11 @@ void DeviceCtx::forward(const MetaLayout& l, const int32_t* meta_d, uint8_t* let
         const LayerW& L = layers[i];
         gemm(Epi::StoreF16, tm_xn, L.tm_qkv, qkv.p, 3 * inner, d);
         prof_begin(PC_ATTN);
-        launch_attention(stream, qkv.as<__half>(), ctx.as<__half>(), cu, aw, l.n_aw, bias, hp.n_head, hp.max_distance);
+        if (opt.attn_impl == 1 && e_ext)
+            launch_attention_tc(stream, num_sms, tm_q, tm_kv, ctx.as<__half>(), cu, aw128, l.n_aw128, e_ext, hp.n_head,
+                                hp.max_distance);
+        else
+            launch_attention(stream, qkv.as<__half>(), ctx.as<__half>(), cu, aw, l.n_aw, bias, hp.n_head, hp.max_distance);
         prof_end();
         gemm(Epi::AddF32, tm_ctx, L.tm_o, h.p, d, inner);
         prof_begin(PC_NORM);

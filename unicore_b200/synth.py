@@ -47,10 +47,11 @@ def make_tensor(name: str, shape: tuple, dtype: str, cfg: spec.ProstT5Config, se
         out[s:s + len(x)] = x
     out = out.reshape(shape)
     if name == "cnn.conv1.weight":
-        # zero-sum filters per class: conv0's ReLU output is non-negative, so a class whose weights sum
-        # high would win almost every residue; centring makes the 20 letters comparably frequent
+        # zero-sum over the taps of every (class, channel) filter: conv0's ReLU output is non-negative with
+        # channel-specific means, so un-centred filters let one class win almost every residue; centred
+        # ones respond to the variation along the sequence and the 20 letters become comparably frequent
         x = out.astype(np.float32)
-        out = (x - x.mean(axis=(1, 2), keepdims=True)).astype(out.dtype)
+        out = (x - x.mean(axis=2, keepdims=True)).astype(out.dtype)
     return out
 
 
