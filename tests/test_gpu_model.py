@@ -191,3 +191,24 @@ def test_config2_properties(full):
     for i in (0, 100, 255):
         s = aa[int(off[i]):int(off[i + 1])].tobytes()
         assert full.encode_debug(s)[2] == a[int(off[i]):int(off[i + 1])].tobytes()
+
+
+def test_in_process_multi_device(tiny_dir):
+    """Two devices in one process (threads + shared batch queue) give the bytes of one device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.default_rng(31)
+    seqs = [random_protein(rng, int(L)) for L in rng.integers(2, 400, 200)]
+    aa, off = pack_sequences(seqs)
+    with Predictor(tiny_dir, devices=[0]) as p:
+        p.set_option("max_batch_tokens", 2048)
+        want = p.predict_packed(aa, off)
+    with Predictor(tiny_dir, devices=[0, 1]) as p:
+        assert p.info["n_devices"] == 2
+        p.set_option("max_batch_tokens", 2048)
+        np.testing.assert_array_equal(p.predict_packed(aa, off), want)
+        p.stage(aa, off)
+        out = np.zeros(len(aa), np.uint8)
+        p.run_staged(out)
+        np.testing.assert_array_equal(out, want)
