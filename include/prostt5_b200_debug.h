@@ -19,8 +19,9 @@ extern "C" {
 
 /* tcgen05 GEMM  C[M,N] (op)= A[M,K] * B[N,K]^T,  A and B fp16 row-major (K contiguous).
  * variant : 0 = one CTA per 128x256 tile, 1 = CTA pair (cta_group::2) per 256x256 tile
- * epilogue: 0 = C fp16 = acc; 1 = C fp16 = relu(acc); 2 = C fp32 += acc; 3 = C fp32 = acc
- * c_host  : in/out, M*N elements of the epilogue's type (read for epilogue 2)
+ * epilogue: 0 = C fp16 = acc; 1 = C fp16 = relu(acc); 2 = C fp32 += acc; 3 = C fp32 = acc;
+ *           4 = C[M, N/2] fp16 = gelu_new(acc[:, 2i]) * acc[:, 2i+1]  (gated FFN, gate/up rows interleaved in B)
+ * c_host  : in/out, M*N elements of the epilogue's type (M*N/2 for epilogue 4; read for epilogue 2)
  * iters>0 : additionally time `iters` back-to-back launches (CUDA events on the launch stream) and
  *           store the mean milliseconds per launch in *ms_out.  c_host always holds the FIRST result. */
 int p5_dbg_gemm(int device, int variant, int epilogue, uint32_t M, uint32_t N, uint32_t K, const uint16_t* a_host,

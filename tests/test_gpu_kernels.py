@@ -49,6 +49,22 @@ def test_gemm_matches_numpy(variant, epi, M, N, K):
     assert (np.abs(got - ref) <= tol).all(), float(np.abs(got - ref).max())
 
 
+def test_gemm_gated_epilogue():
+    lib = _lib.load()
+    rng = np.random.default_rng(9)
+    M, N, K = 300, 512, 256  # N = 2 * d_ff: gate/up rows interleaved
+    a = (rng.standard_normal((M, K), dtype=np.float32) * 0.5).astype(np.float16)
+    b = (rng.standard_normal((N, K), dtype=np.float32) * 0.2).astype(np.float16)
+    acc = a.astype(np.float32) @ b.astype(np.float32).T
+    g, u = acc[:, 0::2], acc[:, 1::2]
+    ref = 0.5 * g * (1 + np.tanh(np.sqrt(2 / np.pi) * (g + 0.044715 * g ** 3))) * u
+    for variant in (0, 1):
+        c = np.zeros((M, N // 2), np.float16)
+        ms = C.c_float(0)
+        _lib.check(lib.p5_dbg_gemm(0, variant, 4, M, N, K, a.ctypes.data, b.ctypes.data, c.ctypes.data, 0, C.byref(ms)))
+        assert np.abs(c.astype(np.float32) - ref).max() < 2e-3 * max(1.0, np.abs(ref).max())
+
+
 def test_gemm_is_deterministic():
     a, _ = _gemm(1, 0, 1000, 512, 1024, seed=5)
     b, _ = _gemm(1, 0, 1000, 512, 1024, seed=5)

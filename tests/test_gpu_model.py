@@ -66,6 +66,25 @@ def test_tiny_matches_hf_golden(tiny):
         assert np.abs(logits - g[f"relu_logits_{n}"]).max() < 2e-2
 
 
+def test_gated_ffn_model(tmp_path_factory):
+    """A gguf with ffn_gate tensors selects the gated-GELU FFN (T5 v1.1 style) [HF modeling_t5.py:107-128]."""
+    from unicore_b200 import synth
+    cfg = spec.ProstT5Config(**{**spec.TINY.to_dict(), "gated": True})
+    d = synth.model_dir(str(tmp_path_factory.mktemp("p5_gated")), cfg, seed=7)
+    om = O.load_gguf_model(os.path.join(d, spec.WEIGHT_FILE))
+    assert om.cfg.gated
+    g = np.load(GOLDEN)
+    with Predictor(d) as p:
+        assert p.info["gated"] == 1
+        rng = np.random.default_rng(41)
+        for L in (5, 64, 300):
+            _check_against_oracle(p, om, random_protein(rng, L), TINY_HID_TOL, TINY_LOGIT_TOL)
+        for n, s in enumerate(g["seqs"]):
+            hid, logits, _ = p.encode_debug(s.encode())
+            assert np.abs(hid - g[f"gated_hidden_{n}"]).max() < 2e-3
+            assert np.abs(logits - g[f"gated_logits_{n}"]).max() < 2e-2
+
+
 def test_non_standard_residues(tiny, tiny_oracle):
     seq = b"ACDEFGHIKLMNPQRSTVWYXBZUOacdxyz*-.1"
     _check_against_oracle(tiny, tiny_oracle, seq, TINY_HID_TOL, TINY_LOGIT_TOL)
@@ -172,6 +191,14 @@ def test_full_size_matches_oracle(full, full_oracle):
         a, b = _check_against_oracle(full, full_oracle, random_protein(rng, L), FULL_HID_TOL, FULL_LOGIT_TOL)
         mism, total = mism + a, total + b
     assert mism <= 0.02 * total
+
+
+def test_full_size_long_sequence(full, full_oracle):
+    """1,200 residues: more than the 1024-token split default of Foldseek, 19 key tiles per query tile, far
+    off-diagonal tiles on both sides (constant-bias path) and several lazy rescales of the accumulator."""
+    rng = np.random.default_rng(22)
+    a, b = _check_against_oracle(full, full_oracle, random_protein(rng, 1200), FULL_HID_TOL, FULL_LOGIT_TOL)
+    assert a <= 0.02 * b
 
 
 def test_config2_properties(full):

@@ -36,7 +36,7 @@ extern "C" int p5_dbg_gemm(int device, int variant, int epilogue, uint32_t M, ui
                            const uint16_t* a_host, const uint16_t* b_host, void* c_host, int iters, float* ms_out) {
     return guarded([&] {
         P5_REQUIRE(a_host && b_host && c_host, P5_ERR_ARG, "null buffer");
-        P5_REQUIRE(epilogue >= 0 && epilogue <= 3, P5_ERR_ARG, "bad epilogue %d", epilogue);
+        P5_REQUIRE(epilogue >= 0 && epilogue <= 4, P5_ERR_ARG, "bad epilogue %d", epilogue);
         P5_CUDA(cudaSetDevice(device));
         cudaDeviceProp prop;
         P5_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -44,15 +44,16 @@ extern "C" int p5_dbg_gemm(int device, int variant, int epilogue, uint32_t M, ui
                    prop.major, prop.minor);
         gemm_init_device();
         const Epi epi = static_cast<Epi>(epilogue);
-        const bool f16_out = (epi == Epi::StoreF16 || epi == Epi::StoreF16Relu);
-        const size_t c_bytes = size_t(M) * N * (f16_out ? 2 : 4);
+        const bool f16_out = (epi == Epi::StoreF16 || epi == Epi::StoreF16Relu || epi == Epi::GatedGeluF16);
+        const uint32_t ldc = epi == Epi::GatedGeluF16 ? N / 2 : N;
+        const size_t c_bytes = size_t(M) * ldc * (f16_out ? 2 : 4);
         ScratchBuf a(size_t(M) * K * 2), b(size_t(N) * K * 2), c(c_bytes);
         P5_CUDA(cudaMemcpy(a.p, a_host, size_t(M) * K * 2, cudaMemcpyHostToDevice));
         P5_CUDA(cudaMemcpy(b.p, b_host, size_t(N) * K * 2, cudaMemcpyHostToDevice));
         P5_CUDA(cudaMemcpy(c.p, c_host, c_bytes, cudaMemcpyHostToDevice));
         cudaStream_t st;
         P5_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        gemm_fp16(st, prop.multiProcessorCount, variant, epi, a.p, K, b.p, K, c.p, N, M, N, K);
+        gemm_fp16(st, prop.multiProcessorCount, variant, epi, a.p, K, b.p, K, c.p, ldc, M, N, K);
         P5_CUDA(cudaStreamSynchronize(st));
         P5_CUDA(cudaMemcpy(c_host, c.p, c_bytes, cudaMemcpyDeviceToHost));
         if (iters > 0 && ms_out) {
@@ -62,10 +63,10 @@ extern "C" int p5_dbg_gemm(int device, int variant, int epilogue, uint32_t M, ui
             P5_CUDA(cudaEventCreate(&e1));
             CUtensorMap ta = make_kmajor_tensor_map(a.p, M, K, K, kGemmBlockM);
             CUtensorMap tb = make_kmajor_tensor_map(b.p, N, K, K, gemm_b_box_rows(variant));
-            for (int i = 0; i < 3; ++i) gemm_launch(st, prop.multiProcessorCount, variant, epi, ta, tb, c.p, N, M, N, K);
+            for (int i = 0; i < 3; ++i) gemm_launch(st, prop.multiProcessorCount, variant, epi, ta, tb, c.p, ldc, M, N, K);
             P5_CUDA(cudaEventRecord(e0, st));
             for (int i = 0; i < iters; ++i)
-                gemm_launch(st, prop.multiProcessorCount, variant, epi, ta, tb, c.p, N, M, N, K);
+                gemm_launch(st, prop.multiProcessorCount, variant, epi, ta, tb, c.p, ldc, M, N, K);
             P5_CUDA(cudaEventRecord(e1, st));
             P5_CUDA(cudaStreamSynchronize(st));
             float ms = 0.f;
@@ -94,7 +95,7 @@ __global__ void fill_random_f16(__half* p, size_t n, uint32_t seed) {
 extern "C" int p5_dbg_gemm_bench(int device, int variant, int epilogue, uint32_t M, uint32_t N, uint32_t K, int iters,
                                  float* ms_out) {
     return guarded([&] {
-        P5_REQUIRE(epilogue >= 0 && epilogue <= 3 && iters > 0 && ms_out, P5_ERR_ARG, "bad argument");
+        P5_REQUIRE(epilogue >= 0 && epilogue <= 4 && iters > 0 && ms_out, P5_ERR_ARG, "bad argument");
         P5_CUDA(cudaSetDevice(device));
         cudaDeviceProp prop;
         P5_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -102,8 +103,9 @@ extern "C" int p5_dbg_gemm_bench(int device, int variant, int epilogue, uint32_t
                    prop.major, prop.minor);
         gemm_init_device();
         const Epi epi = static_cast<Epi>(epilogue);
-        const bool f16_out = (epi == Epi::StoreF16 || epi == Epi::StoreF16Relu);
-        const size_t c_bytes = size_t(M) * N * (f16_out ? 2 : 4);
+        const bool f16_out = (epi == Epi::StoreF16 || epi == Epi::StoreF16Relu || epi == Epi::GatedGeluF16);
+        const uint32_t ldc = epi == Epi::GatedGeluF16 ? N / 2 : N;
+        const size_t c_bytes = size_t(M) * ldc * (f16_out ? 2 : 4);
         ScratchBuf a(size_t(M) * K * 2), b(size_t(N) * K * 2), c(c_bytes);
         cudaStream_t st;
         P5_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -115,9 +117,9 @@ extern "C" int p5_dbg_gemm_bench(int device, int variant, int epilogue, uint32_t
         P5_CUDA(cudaEventCreate(&e1));
         CUtensorMap ta = make_kmajor_tensor_map(a.p, M, K, K, kGemmBlockM);
         CUtensorMap tb = make_kmajor_tensor_map(b.p, N, K, K, gemm_b_box_rows(variant));
-        for (int i = 0; i < 3; ++i) gemm_launch(st, prop.multiProcessorCount, variant, epi, ta, tb, c.p, N, M, N, K);
+        for (int i = 0; i < 3; ++i) gemm_launch(st, prop.multiProcessorCount, variant, epi, ta, tb, c.p, ldc, M, N, K);
         P5_CUDA(cudaEventRecord(e0, st));
-        for (int i = 0; i < iters; ++i) gemm_launch(st, prop.multiProcessorCount, variant, epi, ta, tb, c.p, N, M, N, K);
+        for (int i = 0; i < iters; ++i) gemm_launch(st, prop.multiProcessorCount, variant, epi, ta, tb, c.p, ldc, M, N, K);
         P5_CUDA(cudaEventRecord(e1, st));
         P5_CUDA(cudaStreamSynchronize(st));
         float ms = 0.f;
@@ -142,18 +144,20 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         P5_CUDA(cudaGetDeviceProperties(&prop, device));
         const uint32_t M = uint32_t(cu_host[n_seq]);
         const size_t inner = size_t(n_head) * kHeadDim;
-        std::vector<int2> work;
+        std::vector<int2> work;   // mma.sync kernel: (seq, q0)
+        std::vector<int4> work4;  // tcgen05 kernel: (tok0, T, q0, 0)
         for (uint32_t s = 0; s < n_seq; ++s) {
             const int T = cu_host[s + 1] - cu_host[s];
             P5_REQUIRE(T >= 1, P5_ERR_ARG, "empty sequence %u", s);
-            for (int q = 0; q < T; q += int(impl ? kAttnTcBlockM : kAttnBlockM)) work.push_back(make_int2(int(s), q));
+            for (int q = 0; q < T; q += int(kAttnBlockM)) work.push_back(make_int2(int(s), q));
+            for (int q = 0; q < T; q += int(kAttnTcBlockM)) work4.push_back(make_int4(cu_host[s], T, q, 0));
         }
         const size_t Mpad = (size_t(M) + 255) / 256 * 256;  // TMA boxes may reach past the last sequence: zero rows
         std::vector<float> e_host(size_t(n_head) * kAttnTcTable);
         attention_tc_build_table(bias_host, n_head, max_dist, e_host.data());
         ScratchBuf e_ext(e_host.size() * 4);
         P5_CUDA(cudaMemcpy(e_ext.p, e_host.data(), e_host.size() * 4, cudaMemcpyHostToDevice));
-        ScratchBuf qkv(Mpad * 3 * inner * 2), ctx(M * inner * 2), cu((n_seq + 1) * 4), wk(work.size() * sizeof(int2)),
+        ScratchBuf qkv(Mpad * 3 * inner * 2), ctx(M * inner * 2), cu((n_seq + 1) * 4), wk(work.size() * sizeof(int2)), wk4(work4.size() * sizeof(int4)),
             bias(size_t(n_head) * (2 * max_dist + 1) * 4);
         P5_CUDA(cudaMemset(qkv.p, 0, Mpad * 3 * inner * 2));
         P5_CUDA(cudaMemcpy(qkv.p, qkv_host, M * 3 * inner * 2, cudaMemcpyHostToDevice));
@@ -161,6 +165,7 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         CUtensorMap tm_kv = make_kmajor_tensor_map(qkv.p, Mpad, 3 * inner, 3 * inner, 64);
         P5_CUDA(cudaMemcpy(cu.p, cu_host, (n_seq + 1) * 4, cudaMemcpyHostToDevice));
         P5_CUDA(cudaMemcpy(wk.p, work.data(), work.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        P5_CUDA(cudaMemcpy(wk4.p, work4.data(), work4.size() * sizeof(int4), cudaMemcpyHostToDevice));
         P5_CUDA(cudaMemcpy(bias.p, bias_host, size_t(n_head) * (2 * max_dist + 1) * 4, cudaMemcpyHostToDevice));
         P5_CUDA(cudaMemset(ctx.p, 0, M * inner * 2));
         cudaStream_t st;
@@ -168,8 +173,8 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         auto run = [&] {
             if (impl == 1) {
                 launch_attention_tc(st, prop.multiProcessorCount, tm_q, tm_kv, static_cast<__half*>(ctx.p),
-                                    static_cast<const int32_t*>(cu.p), static_cast<const int2*>(wk.p),
-                                    uint32_t(work.size()), static_cast<const float*>(e_ext.p), n_head, max_dist);
+                                    static_cast<const int4*>(wk4.p), uint32_t(work4.size()),
+                                    static_cast<const float*>(e_ext.p), n_head, max_dist);
                 return;
             }
             launch_attention(st, static_cast<const __half*>(qkv.p), static_cast<__half*>(ctx.p),

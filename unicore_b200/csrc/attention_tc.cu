@@ -48,27 +48,38 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+__device__ __forceinline__ float lds_f32(uint32_t addr) {  // explicit ld.shared (a generic LD costs an extra hop)
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 struct Item {
     int tok0, T, q0, h;
     uint32_t nt;
 };
-__device__ __forceinline__ Item get_item(uint32_t item, uint32_t H, const int2* __restrict__ work,
-                                         const int32_t* __restrict__ cu) {
-    const uint32_t w = item / H;
-    const int2 wk = work[w];
+// Items are head-major (item = h * n_work + w): a persistent CTA keeps its head for several items (the
+// bias table stays in smem) while the CTAs running at the same time cover neighbouring query tiles of the
+// same sequences, whose K/V tiles they share through L2.  work[w] = (first token, tokens, first query row).
+__device__ __forceinline__ Item get_item(uint32_t item, uint32_t n_work, const int4* __restrict__ work) {
+    const uint32_t h = item / n_work;
+    const int4 wk = __ldg(work + (item - h * n_work));
     Item it;
-    it.h = int(item - w * H);
-    it.tok0 = cu[wk.x];
-    it.T = cu[wk.x + 1] - it.tok0;
-    it.q0 = wk.y;
+    it.h = int(h);
+    it.tok0 = wk.x;
+    it.T = wk.y;
+    it.q0 = wk.z;
     it.nt = uint32_t(it.T + int(kBN) - 1) / kBN;
     return it;
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-                    __half* __restrict__ ctx, const int32_t* __restrict__ cu, const int2* __restrict__ work,
-                    uint32_t n_items, uint32_t H, const float* __restrict__ e_ext) {
+                    __half* __restrict__ ctx, const int4* __restrict__ work, uint32_t n_work, uint32_t n_items,
+                    uint32_t H, const float* __restrict__ e_ext) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
@@ -85,7 +96,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                                     // the same barrier (tile g-2) is always known to be complete (S_g was seen)
     uint64_t* o_empty = bars + 16;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + kNumBars);
-    float* e_smem = reinterpret_cast<float*>(smem + kSmemE);
+    const uint32_t e_smem = ptx::smem_u32(smem + kSmemE);  // two bias tables of kEPad floats
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = ptx::lane_id();
@@ -126,7 +137,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if (lane == 0) {
             uint32_t g = 0, n = 0;
             for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
-                const Item it = get_item(item, H, work, cu);
+                const Item it = get_item(item, n_work, work);
                 const int32_t qcol = it.h * int(kD);
                 const int32_t kcol = int(H * kD) + qcol;
                 const int32_t vcol = 2 * int(H * kD) + qcol;
@@ -174,7 +185,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 ptx::umma_commit<1>(&pv_done[st]);
             };
             for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
-                const Item it = get_item(item, H, work, cu);
+                const Item it = get_item(item, n_work, work);
                 ptx::mbar_wait(q_full, n & 1);
                 ptx::tc_fence_after();
                 for (uint32_t j = 0; j < it.nt; ++j, ++g) {
@@ -201,14 +212,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         // =============================== softmax warps ===============================
         const uint32_t r = warp * 32 + lane;  // row of the tile == TMEM lane
         const uint32_t t_lane = tmem_base + ((warp * 32u) << 16);
-        uint32_t g = 0, n = 0;
+        uint32_t g = 0, n = 0, e_buf = 0;
+        int cur_h = -1;
+        uint32_t es = e_smem;
+        float e_lo = 0.f, e_hi = 0.f;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
-            const Item it = get_item(item, H, work, cu);
-            float* es = e_smem + (n & 1) * kEPad;
-            for (uint32_t i = threadIdx.x; i < 2 * kEHalf + 1; i += 128) es[i] = e_ext[size_t(it.h) * kEPad + i];
-            ptx::named_bar_sync(1, 128);
+            const Item it = get_item(item, n_work, work);
+            if (it.h != cur_h) {
+                // other warps may still read the current table: write the other buffer, then meet
+                cur_h = it.h;
+                e_buf ^= 1;
+                es = e_smem + e_buf * kEPad * 4;
+                for (uint32_t i = threadIdx.x; i < 2 * kEHalf + 1; i += 128)
+                    sts_f32(es + i * 4, __ldg(e_ext + size_t(it.h) * kEPad + i));
+                ptx::named_bar_sync(1, 128);
+                e_lo = lds_f32(es);
+                e_hi = lds_f32(es + 2 * kEHalf * 4);
+            }
             const int row_seq = it.q0 + int(r);
-            const float e_lo = es[0], e_hi = es[2 * kEHalf];
             float m = -INFINITY, l = 0.f;
             for (uint32_t j = 0; j < it.nt; ++j, ++g) {
                 const uint32_t b = g & 1, ph = (g >> 1) & 1;
@@ -230,11 +251,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                         z[32 + c] = fmaf(__uint_as_float(v1[c]), kLog2e, e);
                     }
                 } else {
-                    const float* er = es + (int(kEHalf) - row_seq + j0);
+                    const uint32_t er = es + uint32_t(int(kEHalf) - row_seq + j0) * 4;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
-                        z[c] = fmaf(__uint_as_float(v0[c]), kLog2e, er[c]);
-                        z[32 + c] = fmaf(__uint_as_float(v1[c]), kLog2e, er[32 + c]);
+                        z[c] = fmaf(__uint_as_float(v0[c]), kLog2e, lds_f32(er + c * 4));
+                        z[32 + c] = fmaf(__uint_as_float(v1[c]), kLog2e, lds_f32(er + (32 + c) * 4));
                     }
                 }
                 if (j0 + int(kBN) > it.T) {
@@ -242,9 +263,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     for (int c = 0; c < 64; ++c)
                         if (j0 + c >= it.T) z[c] = -INFINITY;
                 }
-                float mx = z[0];
+                float mxa = z[0], mxb = z[1], mxc = z[2], mxd = z[3];  // four independent chains
 #pragma unroll
-                for (int c = 1; c < 64; ++c) mx = fmaxf(mx, z[c]);
+                for (int c = 4; c < 64; c += 4) {
+                    mxa = fmaxf(mxa, z[c]);
+                    mxb = fmaxf(mxb, z[c + 1]);
+                    mxc = fmaxf(mxc, z[c + 2]);
+                    mxd = fmaxf(mxd, z[c + 3]);
+                }
+                const float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
                 if (j == 0) {
                     m = mx;  // key 0 is always valid, so mx is finite
                 } else if (__any_sync(0xffffffffu, mx > m + kRescaleThreshold)) {
@@ -267,14 +294,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     ptx::tmem_st_wait();
                 }
                 uint32_t pk[32];
-                float sum = 0.f;
+                float sa = 0.f, sb = 0.f, sc = 0.f, sd = 0.f;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
+                for (int c = 0; c < 32; c += 2) {
                     const float p0 = ex2(z[2 * c] - m), p1 = ex2(z[2 * c + 1] - m);
-                    sum += p0 + p1;
+                    const float p2 = ex2(z[2 * c + 2] - m), p3 = ex2(z[2 * c + 3] - m);
+                    sa += p0; sb += p1; sc += p2; sd += p3;
                     pk[c] = pack_h2(p0, p1);
+                    pk[c + 1] = pack_h2(p2, p3);
                 }
-                l += sum;
+                l += (sa + sb) + (sc + sd);
                 ptx::tmem_st_32x32b_x32(t_lane + 128 + b * kBN, pk);  // P over the first 32 columns of S
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
@@ -289,19 +318,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             const float inv = 1.f / l;
             __half* dst = ctx + size_t(it.tok0 + row_seq) * (size_t(H) * kD) + size_t(it.h) * kD;
 #pragma unroll 1
-            for (uint32_t c = 0; c < kD / 32; ++c) {
-                uint32_t o[32];
-                ptx::tmem_ld_32x32b_x32(t_lane + c * 32, o);
+            for (uint32_t c = 0; c < kD / 64; ++c) {
+                uint32_t o0[32], o1[32];
+                ptx::tmem_ld_32x32b_x32(t_lane + c * 64, o0);
+                ptx::tmem_ld_32x32b_x32(t_lane + c * 64 + 32, o1);
                 ptx::tmem_ld_wait();
                 if (row_seq < it.T) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         uint4 u;
-                        u.x = pack_h2(__uint_as_float(o[8 * q + 0]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
-                        u.y = pack_h2(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
-                        u.z = pack_h2(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
-                        u.w = pack_h2(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
-                        *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = u;
+                        u.x = pack_h2(__uint_as_float(o0[8 * q + 0]) * inv, __uint_as_float(o0[8 * q + 1]) * inv);
+                        u.y = pack_h2(__uint_as_float(o0[8 * q + 2]) * inv, __uint_as_float(o0[8 * q + 3]) * inv);
+                        u.z = pack_h2(__uint_as_float(o0[8 * q + 4]) * inv, __uint_as_float(o0[8 * q + 5]) * inv);
+                        u.w = pack_h2(__uint_as_float(o0[8 * q + 6]) * inv, __uint_as_float(o0[8 * q + 7]) * inv);
+                        *reinterpret_cast<uint4*>(dst + c * 64 + q * 8) = u;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 u;
+                        u.x = pack_h2(__uint_as_float(o1[8 * q + 0]) * inv, __uint_as_float(o1[8 * q + 1]) * inv);
+                        u.y = pack_h2(__uint_as_float(o1[8 * q + 2]) * inv, __uint_as_float(o1[8 * q + 3]) * inv);
+                        u.z = pack_h2(__uint_as_float(o1[8 * q + 4]) * inv, __uint_as_float(o1[8 * q + 5]) * inv);
+                        u.w = pack_h2(__uint_as_float(o1[8 * q + 6]) * inv, __uint_as_float(o1[8 * q + 7]) * inv);
+                        *reinterpret_cast<uint4*>(dst + c * 64 + 32 + q * 8) = u;
                     }
                 }
             }
@@ -334,15 +373,14 @@ void attention_tc_build_table(const float* bias, uint32_t H, uint32_t max_dist, 
 }
 
 void launch_attention_tc(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, const CUtensorMap& tm_kv, __half* ctx,
-                         const int32_t* cu, const int2* work128, uint32_t n_work, const float* e_ext, uint32_t H,
-                         uint32_t max_dist) {
+                         const int4* work128, uint32_t n_work, const float* e_ext, uint32_t H, uint32_t max_dist) {
     if (n_work == 0) return;
     P5_REQUIRE(max_dist <= 128, P5_ERR_UNSUPPORTED,
                "relative attention max distance %u: the tcgen05 attention kernel assumes <= 128", max_dist);
     const uint64_t n_items = uint64_t(n_work) * H;
     P5_REQUIRE(n_items < (1ull << 31), P5_ERR_UNSUPPORTED, "too many attention work items");
     const uint32_t grid = uint32_t(std::min<uint64_t>(n_items, uint64_t(2 * num_sms)));
-    attention_tc_kernel<<<grid, kThreads, kSmemDynamic, st>>>(tm_q, tm_kv, ctx, cu, work128, uint32_t(n_items), H, e_ext);
+    attention_tc_kernel<<<grid, kThreads, kSmemDynamic, st>>>(tm_q, tm_kv, ctx, work128, n_work, uint32_t(n_items), H, e_ext);
     P5_CUDA(cudaGetLastError());
 }
 

@@ -21,18 +21,24 @@ enum class Epi : int {
     StoreF16Relu = 1,  // C = fp16(max(acc,0))            (FFN-in, p8)
     AddF32 = 2,        // C(fp32) += acc                  (residual add of O / FFN-out, p7/p8)
     StoreF32 = 3,      // C(fp32) = acc                   (conv-head taps, p10)
+    GatedGeluF16 = 4,  // C[:, i] = fp16(gelu_new(acc[:, 2i]) * acc[:, 2i+1]): gate/up rows interleaved in B
+                       // (gated T5 v1.1 FFN, p8 variant); C has N/2 columns
 };
+
+__device__ __forceinline__ float gelu_new(float x) {  // HF "gelu_new" (tanh approximation)
+    return 0.5f * x * (1.f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+}
 
 struct GemmShape {
     uint32_t M, N, K;
-    uint32_t ldc;  // elements
+    uint32_t ldc;     // elements
+    uint32_t band_m;  // m-tiles per L2 band of the tile order
 };
 
 constexpr uint32_t kGemmBlockM = 128;  // rows per CTA (= TMEM lanes)
 constexpr uint32_t kGemmBlockK = 64;   // 64 fp16 = one 128-byte swizzle atom
 constexpr uint32_t kUmmaK = 16;
 constexpr uint32_t kGemmThreads = 256;
-constexpr uint32_t kBandM = 8;  // m-tiles per L2 band of the tile order
 
 template <int kCtaGroup, int kBlockN, int kStages>
 struct GemmSmem {
@@ -46,7 +52,7 @@ struct GemmSmem {
     static constexpr uint32_t kDynamic = kTotal + 1024;  // slack for manual 1024 B alignment
 };
 
-__device__ __forceinline__ void tile_coords(uint32_t t, uint32_t num_mt, uint32_t num_nt, uint32_t& mt,
+__device__ __forceinline__ void tile_coords(uint32_t t, uint32_t num_mt, uint32_t num_nt, uint32_t kBandM, uint32_t& mt,
                                             uint32_t& nt) {
     const uint32_t band_tiles = kBandM * num_nt;
     const uint32_t band = t / band_tiles;
@@ -120,7 +126,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters) {
                 uint32_t mt, nt;
-                tile_coords(t, num_mt, num_nt, mt, nt);
+                tile_coords(t, num_mt, num_nt, s.band_m, mt, nt);
                 const int32_t m_idx = static_cast<int32_t>((mt * kCtaGroup + cta_rank) * kGemmBlockM);
                 const int32_t n_idx = static_cast<int32_t>(nt * kBlockN + cta_rank * L::kLoadN);
                 for (uint32_t kb = 0; kb < num_kb; ++kb) {
@@ -179,7 +185,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         uint32_t accum_iter = 0;
         for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++accum_iter) {
             uint32_t mt, nt;
-            tile_coords(t, num_mt, num_nt, mt, nt);
+            tile_coords(t, num_mt, num_nt, s.band_m, mt, nt);
             const uint32_t as = accum_iter & 1u;
             const uint32_t aphase = (accum_iter >> 1) & 1u;
             const uint32_t row = (mt * kCtaGroup + cta_rank) * kGemmBlockM + ew * 32 + lane;
@@ -195,7 +201,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 const uint32_t col0 = n_base + c * 32;
                 if (row < s.M && col0 < s.N) {
                     const uint32_t ncols = min(32u, s.N - col0);  // multiple of 8 (checked on host)
-                    if constexpr (kEpi == Epi::StoreF16 || kEpi == Epi::StoreF16Relu) {
+                    if constexpr (kEpi == Epi::GatedGeluF16) {
+                        __half* crow = reinterpret_cast<__half*>(Cptr) + static_cast<size_t>(row) * s.ldc + (col0 >> 1);
+#pragma unroll
+                        for (uint32_t j = 0; j < 2; ++j) {
+                            if (j * 16 < ncols) {
+                                uint32_t pk[4];
+#pragma unroll
+                                for (uint32_t q = 0; q < 4; ++q) {
+                                    const float g0 = __uint_as_float(v[j * 16 + 4 * q]), u0 = __uint_as_float(v[j * 16 + 4 * q + 1]);
+                                    const float g1 = __uint_as_float(v[j * 16 + 4 * q + 2]), u1 = __uint_as_float(v[j * 16 + 4 * q + 3]);
+                                    __half2 h = __floats2half2_rn(gelu_new(g0) * u0, gelu_new(g1) * u1);
+                                    pk[q] = *reinterpret_cast<uint32_t*>(&h);
+                                }
+                                *reinterpret_cast<uint4*>(crow + j * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                        }
+                    } else if constexpr (kEpi == Epi::StoreF16 || kEpi == Epi::StoreF16Relu) {
                         __half* crow = reinterpret_cast<__half*>(Cptr) + static_cast<size_t>(row) * s.ldc + col0;
 #pragma unroll
                         for (uint32_t j = 0; j < 4; ++j) {

@@ -4,6 +4,7 @@
 
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.h"
@@ -87,6 +88,7 @@ void launch_epi(cudaStream_t stream, int num_sms, Epi epi, const CUtensorMap& ta
         case Epi::StoreF16Relu: launch_one<kCtaGroup, kBlockN, kStages, Epi::StoreF16Relu>(stream, num_sms, ta, tb, C, s); break;
         case Epi::AddF32: launch_one<kCtaGroup, kBlockN, kStages, Epi::AddF32>(stream, num_sms, ta, tb, C, s); break;
         case Epi::StoreF32: launch_one<kCtaGroup, kBlockN, kStages, Epi::StoreF32>(stream, num_sms, ta, tb, C, s); break;
+        case Epi::GatedGeluF16: launch_one<kCtaGroup, kBlockN, kStages, Epi::GatedGeluF16>(stream, num_sms, ta, tb, C, s); break;
     }
 }
 
@@ -101,6 +103,8 @@ void init_variant() {
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kDynamic));
     P5_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kCtaGroup, kBlockN, kStages, Epi::StoreF32>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kDynamic));
+    P5_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kCtaGroup, kBlockN, kStages, Epi::GatedGeluF16>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kDynamic));
 }
 
 }  // namespace
@@ -109,12 +113,14 @@ void init_variant() {
 void gemm_init_device() {
     init_variant<1, 256, 4>();
     init_variant<2, 256, 6>();
+
 }
 
 uint32_t gemm_b_box_rows(int variant) {
     switch (variant) {
         case 0: return 256;  // 1 CTA, full 256-row B tile
         case 1: return 128;  // CTA pair, each CTA loads half of the 256-row B tile
+
         default: throw Error(P5_ERR_ARG, strf("unknown GEMM variant %d", variant));
     }
 }
@@ -122,14 +128,21 @@ uint32_t gemm_b_box_rows(int variant) {
 void gemm_launch(cudaStream_t stream, int num_sms, int variant, Epi epi, const CUtensorMap& tma_a,
                  const CUtensorMap& tma_b, void* C, uint32_t ldc, uint32_t M, uint32_t N, uint32_t K) {
     P5_REQUIRE(N % 8 == 0 && K % 8 == 0, P5_ERR_ARG, "GEMM N (%u) and K (%u) must be multiples of 8", N, K);
-    const bool f16_out = (epi == Epi::StoreF16 || epi == Epi::StoreF16Relu);
+    const bool f16_out = (epi == Epi::StoreF16 || epi == Epi::StoreF16Relu || epi == Epi::GatedGeluF16);
+    P5_REQUIRE(epi != Epi::GatedGeluF16 || N % 16 == 0, P5_ERR_ARG, "gated GEMM needs N (%u) to be a multiple of 16", N);
     P5_REQUIRE((ldc * (f16_out ? 2u : 4u)) % 16 == 0, P5_ERR_ARG, "GEMM ldc (%u) breaks 16-byte row alignment", ldc);
     P5_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0, P5_ERR_ARG, "GEMM output is not 16-byte aligned");
-    GemmShape s{M, N, K, ldc};
+    static const uint32_t band = [] {
+        const char* e = getenv("P5_GEMM_BAND");
+        const int v = e ? atoi(e) : 8;
+        return uint32_t(v >= 1 ? v : 8);
+    }();
+    GemmShape s{M, N, K, ldc, band};
     if (M == 0 || N == 0) return;
     switch (variant) {
         case 0: launch_epi<1, 256, 4>(stream, num_sms, epi, tma_a, tma_b, C, s); break;
         case 1: launch_epi<2, 256, 6>(stream, num_sms, epi, tma_a, tma_b, C, s); break;
+
         default: throw Error(P5_ERR_ARG, strf("unknown GEMM variant %d", variant));
     }
 }

@@ -94,7 +94,7 @@ static void finish_layout(Batch& b) {
     l.off_cu = align4(l.M);
     l.off_aw = l.off_cu + align4(l.S + 1);
     l.off_aw128 = l.off_aw + align4(2 * l.n_aw);
-    l.off_hw = l.off_aw128 + align4(2 * l.n_aw128);
+    l.off_hw = l.off_aw128 + 4 * l.n_aw128;
     l.words = l.off_hw + align4(2 * l.n_hw);
 }
 
@@ -159,7 +159,10 @@ static void build_meta(const Model& m, const Batch& b, const uint8_t* aa, int32_
         ids[tok++] = m.hp.eos_id;
         const uint32_t T = u.len + 2;
         for (uint32_t q = 0; q < T; q += kAttnBlockM) { aw[2 * na] = int32_t(s); aw[2 * na + 1] = int32_t(q); ++na; }
-        for (uint32_t q = 0; q < T; q += kAttnTcBlockM) { aw2[2 * na2] = int32_t(s); aw2[2 * na2 + 1] = int32_t(q); ++na2; }
+        for (uint32_t q = 0; q < T; q += kAttnTcBlockM) {
+            aw2[4 * na2] = cu[s]; aw2[4 * na2 + 1] = int32_t(T); aw2[4 * na2 + 2] = int32_t(q); aw2[4 * na2 + 3] = 0;
+            ++na2;
+        }
         for (uint32_t r = 0; r < u.len; r += kHeadChunk) { hw[2 * nh] = int32_t(s); hw[2 * nh + 1] = int32_t(r); ++nh; }
     }
     cu[l.S] = int32_t(tok);
@@ -360,7 +363,21 @@ void DeviceCtx::init(int device, const Model* m, const GgufFile& g) {
             return upload<__half>(v.data(), v.size() * 2);
         };
         L.wo = mat(p + "attn_o.weight", d, inner);
-        L.wi = mat(p + "ffn_up.weight", ff, d);
+        if (hp.gated) {  // rows interleaved gate_0, up_0, gate_1, up_1, ...: one GEMM + gated epilogue
+            const GgufTensor& tg = g.tensor(p + "ffn_gate.weight");
+            const GgufTensor& tu = g.tensor(p + "ffn_up.weight");
+            expect_shape(g, tg, {ff, d});
+            expect_shape(g, tu, {ff, d});
+            auto vg = tensor_f16(tg), vu = tensor_f16(tu);
+            std::vector<__half> inter(size_t(2) * ff * d);
+            for (uint32_t r = 0; r < ff; ++r) {
+                memcpy(&inter[size_t(2 * r) * d], &vg[size_t(r) * d], size_t(d) * 2);
+                memcpy(&inter[size_t(2 * r + 1) * d], &vu[size_t(r) * d], size_t(d) * 2);
+            }
+            L.wi = upload<__half>(inter.data(), inter.size() * 2);
+        } else {
+            L.wi = mat(p + "ffn_up.weight", ff, d);
+        }
         L.wdown = mat(p + "ffn_down.weight", d, ff);
     }
     {
@@ -401,7 +418,7 @@ void DeviceCtx::build_weight_maps() {
     for (LayerW& L : layers) {
         L.tm_qkv = make_kmajor_tensor_map(L.wqkv, 3 * inner, d, d, brows);
         L.tm_o = make_kmajor_tensor_map(L.wo, d, inner, inner, brows);
-        L.tm_i = make_kmajor_tensor_map(L.wi, ff, d, d, brows);
+        L.tm_i = make_kmajor_tensor_map(L.wi, (hp.gated ? 2 : 1) * ff, d, d, brows);
         L.tm_down = make_kmajor_tensor_map(L.wdown, d, ff, ff, brows);
     }
     tm_c0 = make_kmajor_tensor_map(wc0, hp.cnn_kernel * hp.cnn_hidden, d, d, brows);
@@ -468,11 +485,11 @@ void DeviceCtx::forward(const MetaLayout& l, const int32_t* meta_d, uint8_t* let
     const int32_t* ids = meta_d + l.off_ids;
     const int32_t* cu = meta_d + l.off_cu;
     const int2* aw = reinterpret_cast<const int2*>(meta_d + l.off_aw);
-    const int2* aw128 = reinterpret_cast<const int2*>(meta_d + l.off_aw128);
+    const int4* aw128 = reinterpret_cast<const int4*>(meta_d + l.off_aw128);
     const int2* hw = reinterpret_cast<const int2*>(meta_d + l.off_hw);
     auto gemm = [&](Epi epi, const CUtensorMap& ta, const CUtensorMap& tb, void* C, uint32_t N, uint32_t K) {
         prof_begin(PC_GEMM);
-        gemm_launch(stream, num_sms, opt.gemm_variant, epi, ta, tb, C, N, M, N, K);
+        gemm_launch(stream, num_sms, opt.gemm_variant, epi, ta, tb, C, epi == Epi::GatedGeluF16 ? N / 2 : N, M, N, K);
         prof_end();
         stats.gemm_launches += 1;
         stats.gemm_flops += 2.0 * M * double(N) * K;
@@ -485,7 +502,7 @@ void DeviceCtx::forward(const MetaLayout& l, const int32_t* meta_d, uint8_t* let
         gemm(Epi::StoreF16, tm_xn, L.tm_qkv, qkv.p, 3 * inner, d);
         prof_begin(PC_ATTN);
         if (opt.attn_impl == 1 && e_ext)
-            launch_attention_tc(stream, num_sms, tm_q, tm_kv, ctx.as<__half>(), cu, aw128, l.n_aw128, e_ext, hp.n_head,
+            launch_attention_tc(stream, num_sms, tm_q, tm_kv, ctx.as<__half>(), aw128, l.n_aw128, e_ext, hp.n_head,
                                 hp.max_distance);
         else
             launch_attention(stream, qkv.as<__half>(), ctx.as<__half>(), cu, aw, l.n_aw, bias, hp.n_head, hp.max_distance);
@@ -494,7 +511,8 @@ void DeviceCtx::forward(const MetaLayout& l, const int32_t* meta_d, uint8_t* let
         prof_begin(PC_NORM);
         launch_rmsnorm(stream, h.as<float>(), L.ffn_norm, hp.eps, xn.as<__half>(), nullptr, M, d);
         prof_end();
-        gemm(Epi::StoreF16Relu, tm_xn, L.tm_i, ffn.p, ff, d);
+        if (hp.gated) gemm(Epi::GatedGeluF16, tm_xn, L.tm_i, ffn.p, 2 * ff, d);
+        else gemm(Epi::StoreF16Relu, tm_xn, L.tm_i, ffn.p, ff, d);
         gemm(Epi::AddF32, tm_ffn, L.tm_down, h.p, d, ff);
         const bool last = i + 1 == hp.n_layer;
         prof_begin(PC_NORM);
@@ -574,8 +592,6 @@ Model* model_load(const std::string& dir, const int* devices, int n_devices) {
     expect_shape(g, c0, {hp.cnn_hidden, hp.d_model, hp.cnn_kernel});
     expect_shape(g, c1, {hp.cnn_classes, hp.cnn_hidden, hp.cnn_kernel});
     P5_REQUIRE(hp.d_kv == kHeadDim, P5_ERR_UNSUPPORTED, "attention head size %u: the kernels are specialised on 128", hp.d_kv);
-    P5_REQUIRE(!hp.gated, P5_ERR_UNSUPPORTED,
-               "%s holds a gated FFN (ffn_gate tensors); ProstT5 is dense-ReLU and the gated epilogue is not built yet", path.c_str());
     P5_REQUIRE(hp.d_model % 8 == 0 && hp.d_ff % 8 == 0 && hp.n_layer >= 1, P5_ERR_UNSUPPORTED, "unsupported model dimensions");
     P5_REQUIRE(hp.cnn_classes <= 20, P5_ERR_UNSUPPORTED, "the 3Di alphabet has 20 letters, the head has %u classes", hp.cnn_classes);
 
