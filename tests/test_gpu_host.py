@@ -87,3 +87,23 @@ def test_foldseek_shim_createdb(tmp_path, tiny_dir, tiny_oracle):
     p = subprocess.run([SHIM, "createdb", str(fasta), str(db), "--prostt5-model", str(tmp_path / "nope")],
                        capture_output=True, text=True)
     assert p.returncode == 1 and "prostt5-f16.gguf" in p.stderr
+
+
+def test_custom_lookup_partial(tmp_path, tiny_dir, tiny_oracle):
+    """Sequences found in the lookup DB take its 3Di verbatim; the others are predicted on the GPU."""
+    rng = np.random.default_rng(8)
+    seqs = [random_protein(rng, int(L)).decode() for L in (30, 77, 150, 260)]
+    (tmp_path / "in").mkdir()
+    (tmp_path / "in" / "Sp.fa").write_text("".join(f">p{i}\n{s}\n" for i, s in enumerate(seqs)))
+    look = str(tmp_path / "look")
+    for suffix, rows in (("", [seqs[1], seqs[3]]), ("_ss", ["V" * len(seqs[1]), "L" * len(seqs[3])])):
+        with open(look + suffix, "wb") as f:
+            for r in rows:
+                f.write(r.encode() + b"\n\0")
+    out = tmp_path / "o" / "db"
+    p = subprocess.run([UNICORE, "createdb", str(tmp_path / "in"), str(out), tiny_dir, "--custom-lookup", look],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    entries = {aa: ss for _, aa, ss in H.check_foldseek_db(str(out))}
+    assert entries[seqs[1]] == "V" * len(seqs[1]) and entries[seqs[3]] == "L" * len(seqs[3])
+    _check_ss([(H.hashed_name(s), s, entries[s]) for s in (seqs[0], seqs[2])], tiny_oracle)

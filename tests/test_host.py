@@ -166,3 +166,33 @@ def test_example_data_map_matches_golden(tmp_path, tiny_dir):
     assert len(lines) == gold["map_lines"] == 1276
     assert hashlib.md5("".join(lines).encode()).hexdigest() == gold["map_sorted_md5"]
     assert [l.rstrip("\n") for l in lines[:3]] == gold["first_sorted_lines"]
+
+
+def _write_lookup_db(db, entries):
+    """entries: [(aa, ss)] -> minimal Foldseek DB pair <db>, <db>_ss as read_db sees them."""
+    with open(db, "wb") as f:
+        for aa, _ in entries:
+            f.write(aa.encode() + b"\n\0")
+    with open(db + "_ss", "wb") as f:
+        for _, ss in entries:
+            f.write(ss.encode() + b"\n\0")
+
+
+def test_custom_lookup_all_found_needs_no_gpu(tmp_path, tiny_dir):
+    """[REF src/seq/afdb_lookup.rs:131-181] every sequence is in the lookup DB: nothing is predicted, the DB is
+    written from the table alone (this path never touches the device, so it runs here)."""
+    inp = _make_inputs(tmp_path / "in")
+    data, lines = H.collect(str(inp), max_len=200)
+    table = [(aa, "D" * len(aa)) for aa in data.values()] + [("MKV", "AAA")]
+    look = str(tmp_path / "lookdb")
+    _write_lookup_db(look, table)
+    out = tmp_path / "o" / "db"
+    p = _run([UNICORE, "createdb", str(inp), str(out), tiny_dir, "--max-len", "200", "--custom-lookup", look])
+    assert p.returncode == 0, p.stderr
+    assert "2 sequences found from the lookup database" in p.stdout
+    entries = H.check_foldseek_db(str(out))
+    assert [n for n, _, _ in entries] == sorted(data)          # converted entries are header-sorted
+    assert all(aa == data[n] and ss == "D" * len(aa) for n, aa, ss in entries)
+    assert (out.parent / "createdb.chk").read_text() == "1"
+    p = _run([UNICORE, "createdb", str(inp), str(tmp_path / "o2" / "db"), tiny_dir, "--custom-lookup", str(tmp_path / "nodb")])
+    assert p.returncode == 1 and "Custom lookup database does not exist" in p.stderr

@@ -33,6 +33,7 @@ struct GemmShape {
     uint32_t M, N, K;
     uint32_t ldc;     // elements
     uint32_t band_m;  // m-tiles per L2 band of the tile order
+    uint32_t idesc_extra;  // OR-ed into the instruction descriptor (experiments: bf16 operand formats)
 };
 
 constexpr uint32_t kGemmBlockM = 128;  // rows per CTA (= TMEM lanes)
@@ -151,7 +152,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     } else if (warp_idx == 1) {
         // ===================== MMA issuer =====================
         if (is_leader) {
-            constexpr uint32_t idesc = ptx::make_idesc_f16_f32(kUmmaM, kBlockN);
+            const uint32_t idesc = ptx::make_idesc_f16_f32(kUmmaM, kBlockN) | s.idesc_extra;
             uint32_t stage = 0, phase = 0, accum_iter = 0;
             for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++accum_iter) {
                 const uint32_t as = accum_iter & 1u;

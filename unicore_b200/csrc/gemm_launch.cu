@@ -137,7 +137,9 @@ void gemm_launch(cudaStream_t stream, int num_sms, int variant, Epi epi, const C
         const int v = e ? atoi(e) : 8;
         return uint32_t(v >= 1 ? v : 8);
     }();
-    GemmShape s{M, N, K, ldc, band};
+    // P5_GEMM_BF16=1 (timing experiments only): interpret both operands as bf16 (a_format = b_format = 1)
+    static const uint32_t idesc_extra = getenv("P5_GEMM_BF16") ? ((1u << 7) | (1u << 10)) : 0u;
+    GemmShape s{M, N, K, ldc, band, idesc_extra};
     if (M == 0 || N == 0) return;
     switch (variant) {
         case 0: launch_epi<1, 256, 4>(stream, num_sms, epi, tma_a, tma_b, C, s); break;

@@ -319,6 +319,33 @@ std::vector<std::string> read_db(const std::string& path) {
     return out;
 }
 
+void split_by_lookup(const std::string& lookup_db, std::vector<Record>& recs, std::vector<Record>& found,
+                     std::vector<std::string>& found_ss) {
+    const std::string ss_path = lookup_db + "_ss";
+    if (!is_file(lookup_db) || !is_file(ss_path))
+        die(ERR_GENERAL, "Custom lookup database does not exist or improperly formatted.");
+    msg(3, "\nLoading the database...");
+    const std::vector<std::string> aa = read_db(lookup_db), ss = read_db(ss_path);
+    if (aa.size() != ss.size()) die(ERR_GENERAL, "The custom lookup database is not properly formatted.");
+    std::unordered_map<std::string, std::string> table;
+    for (size_t i = 0; i < aa.size(); ++i) table[aa[i]] = ss[i];  // insert: a repeated sequence keeps the last 3Di
+    std::vector<Record> keep;
+    std::vector<std::pair<Record, std::string>> hit;
+    for (Record& r : recs) {
+        auto it = table.find(r.seq);
+        if (it != table.end() && it->second.size() == r.seq.size()) hit.emplace_back(std::move(r), it->second);
+        else keep.push_back(std::move(r));
+    }
+    std::sort(hit.begin(), hit.end(), [](const auto& a, const auto& b) { return a.first.name < b.first.name; });
+    msg(3, std::to_string(hit.size()) + " sequences found from the lookup database");
+    msg(3, std::to_string(keep.size()) + " sequences not found and will be predicted");
+    recs = std::move(keep);
+    for (auto& h : hit) {
+        found.push_back(std::move(h.first));
+        found_ss.push_back(std::move(h.second));
+    }
+}
+
 void write_checkpoint(const std::string& path, const std::string& content) {
     std::ofstream out(path, std::ios::binary | std::ios::trunc);
     out << content;

@@ -54,6 +54,12 @@ void write_foldseek_db(const std::string& db, const std::vector<Record>& recs, c
 // [REF src/seq/create_gene_specific_fasta.rs:9-25]
 std::vector<std::string> read_db(const std::string& path);
 
+// [REF src/seq/afdb_lookup.rs:131-181] run_custom: `lookup_db` and `lookup_db`_ss are read with read_db and
+// zipped into an (amino-acid string -> 3Di string) table; records whose sequence is in the table move to
+// `found` (+ their 3Di in `found_ss`), sorted by name; `recs` keeps the ones that must be predicted.
+void split_by_lookup(const std::string& lookup_db, std::vector<Record>& recs, std::vector<Record>& found,
+                     std::vector<std::string>& found_ss);
+
 // [REF src/util/checkpoint.rs:2-10]
 void write_checkpoint(const std::string& path, const std::string& content);
 std::string read_checkpoint(const std::string& path);

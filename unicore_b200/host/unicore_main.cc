@@ -23,8 +23,8 @@ static const char* kUsage =
     "  -o, --overwrite               Force overwrite output database\n"
     "      --max-len <MAX_LEN>       Set maximum sequence length threshold\n"
     "  -g, --gpu                     Accepted for compatibility (this build always runs on the GPU)\n"
-    "      --afdb-lookup <PATH>      Not implemented in this build\n"
-    "      --custom-lookup <PATH>    Not implemented in this build\n"
+    "      --afdb-lookup <PATH>      Not implemented in this build (needs the 30 GB AFDB tables)\n"
+    "      --custom-lookup <PATH>    Use custom lookup database, accepts any Foldseek database to reference against\n"
     "      --threads <THREADS>       Accepted for compatibility [default: 0]\n"
     "  -v, --verbosity <VERBOSITY>   0: quiet, 1: +errors, 2: +warnings, 3: +info, 4: +debug [default: 3]\n"
     "      --devices <LIST>          Comma-separated CUDA devices (default: all visible)\n"
@@ -74,8 +74,7 @@ static int createdb(int argc, char** argv) {
     const std::string input = pos[0], output = pos[1], model = pos[2];
     if (!afdb.empty() && !custom.empty())
         die(ERR_ARGPARSE, "Both afdb_lookup and custom_lookup are specified. Please specify only one.");
-    if (!afdb.empty() || !custom.empty())
-        die(ERR_MODULE_NOT_IMPLEMENTED, "createdb --afdb-lookup / --custom-lookup (DESIGN.md: next rows f1, f3)");
+    if (!afdb.empty()) die(ERR_MODULE_NOT_IMPLEMENTED, "createdb --afdb-lookup (DESIGN.md: next row f3)");
 
     std::string parent = parent_dir(output);
     if (parent.empty()) parent = ".";
@@ -92,14 +91,24 @@ static int createdb(int argc, char** argv) {
     // The reference builds this path as curr_dir/parent/combined_aa.fasta, which breaks for absolute
     // outputs [REF src/modules/createdb.rs:115-127]; the intermediate belongs next to the output.
     const std::string combined = parent + "/combined_aa.fasta";
-    write_fasta(combined, recs);
 
     if (path_exists(model + "/cnn.safetensors") || path_exists(model + "/model/cnn.safetensors"))
         die(ERR_GENERAL, "Old weight files detected from the given path. Please provide different path for the model weights");
     if (!path_exists(model + "/prostt5-f16.gguf"))
         die(ERR_FILE_NOT_FOUND, model + "/prostt5-f16.gguf (this build does not download weights; run `foldseek databases ProstT5 " +
                                     model + " tmp` where a network exists)");
-    std::vector<std::string> ss = predict_3di(model, recs, popt);
+    // --custom-lookup [REF src/seq/afdb_lookup.rs:131-181]: sequences present in the lookup DB take its 3Di,
+    // only the rest is predicted; the final DB holds the predicted entries followed by the converted ones
+    // (header-sorted), which is what base:createdb + base:concatdbs produce [REF createdb.rs:168-205].
+    std::vector<Record> found;
+    std::vector<std::string> found_ss;
+    if (!custom.empty()) split_by_lookup(custom, recs, found, found_ss);
+    write_fasta(combined, recs);
+    std::vector<std::string> ss;
+    if (!recs.empty()) ss = predict_3di(model, recs, popt);
+    else msg(3, "Every sequence was found in the lookup database: nothing to predict");
+    recs.insert(recs.end(), found.begin(), found.end());
+    ss.insert(ss.end(), found_ss.begin(), found_ss.end());
     write_foldseek_db(output, recs, ss, base_name(combined));
     if (!keep) remove(combined.c_str());
     write_checkpoint(chk, "1");
