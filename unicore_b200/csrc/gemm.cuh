@@ -47,7 +47,10 @@ struct GemmSmem {
     static constexpr uint32_t kABytes = kGemmBlockM * kGemmBlockK * 2;
     static constexpr uint32_t kBBytes = kLoadN * kGemmBlockK * 2;
     static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-    static constexpr uint32_t kBarOffset = kStages * kStageBytes;
+    // epilogue staging: per epilogue warp two 32-row x 128-byte tiles (128B-swizzled, read by TMA stores)
+    static constexpr uint32_t kStagingOffset = kStages * kStageBytes;
+    static constexpr uint32_t kStagingBytes = 4 * 2 * 4096;
+    static constexpr uint32_t kBarOffset = kStagingOffset + kStagingBytes;
     // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem ptr
     static constexpr uint32_t kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16;
     static constexpr uint32_t kDynamic = kTotal + 1024;  // slack for manual 1024 B alignment
@@ -67,7 +70,7 @@ __device__ __forceinline__ void tile_coords(uint32_t t, uint32_t num_mt, uint32_
 template <int kCtaGroup, int kBlockN, int kStages, Epi kEpi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    void* __restrict__ Cptr, GemmShape s) {
+                    const __grid_constant__ CUtensorMap tma_c, void* __restrict__ Cptr, GemmShape s) {
     using L = GemmSmem<kCtaGroup, kBlockN, kStages>;
     constexpr uint32_t kUmmaM = kGemmBlockM * kCtaGroup;
     constexpr uint32_t kTmemCols = 2 * kBlockN;
@@ -93,6 +96,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (warp_idx == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tma_a);
         ptx::prefetch_tensormap(&tma_b);
+        ptx::prefetch_tensormap(&tma_c);
     }
     if (warp_idx == 1 && lane == 0) {
 #pragma unroll
@@ -152,7 +156,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     } else if (warp_idx == 1) {
         // ===================== MMA issuer =====================
         if (is_leader) {
-            const uint32_t idesc = ptx::make_idesc_f16_f32(kUmmaM, kBlockN) | s.idesc_extra;
+            const uint32_t idesc = ptx::make_idesc_f16_f32(kUmmaM, kBlockN) | (s.idesc_extra & 0x7FFFFFFFu);
             uint32_t stage = 0, phase = 0, accum_iter = 0;
             for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++accum_iter) {
                 const uint32_t as = accum_iter & 1u;
@@ -182,27 +186,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
     } else if (warp_idx >= 4) {
         // ===================== epilogue =====================
+        // TMEM -> registers -> fused op -> 128B-swizzled smem tile (32 rows x 128 B per warp, two
+        // buffers) -> TMA store / TMA reduce-add.  Whole 128-byte lines leave the SM asynchronously; the
+        // warp only waits for smem reuse, and the accumulator stage is released right after its last
+        // tcgen05.ld.  (Writing 16 B per row per thread straight to global cost ~30 % of the K=1024
+        // GEMMs: profiles/r01/README.md.)
         const uint32_t ew = warp_idx - 4;  // == warp_idx % 4: the TMEM lane quarter this warp may read
+        uint8_t* stage_base = smem + L::kStagingOffset + ew * 8192;
+        uint32_t sbuf = 0;
         uint32_t accum_iter = 0;
+        constexpr bool kF16Out = (kEpi == Epi::StoreF16 || kEpi == Epi::StoreF16Relu);
         for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++accum_iter) {
             uint32_t mt, nt;
             tile_coords(t, num_mt, num_nt, s.band_m, mt, nt);
             const uint32_t as = accum_iter & 1u;
             const uint32_t aphase = (accum_iter >> 1) & 1u;
-            const uint32_t row = (mt * kCtaGroup + cta_rank) * kGemmBlockM + ew * 32 + lane;
+            const uint32_t row0 = (mt * kCtaGroup + cta_rank) * kGemmBlockM + ew * 32;  // first row of this warp
+            const uint32_t row = row0 + lane;
             const uint32_t n_base = nt * kBlockN;
             ptx::mbar_wait(&tmem_full_bar[as], aphase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((ew * 32u) << 16) + as * kBlockN;
+            auto release_accumulator = [&] {  // stage drained: hand it back to the MMA issuer of the leader CTA
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (kCtaGroup == 1) ptx::mbar_arrive(&tmem_empty_bar[as]);
+                    else ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+                }
+            };
+            if constexpr (kEpi == Epi::GatedGeluF16) {
+                // rare path (gated FFN): direct 128-bit stores, C has N/2 columns
 #pragma unroll 1
-            for (uint32_t c = 0; c < kBlockN / 32; ++c) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
-                ptx::tmem_ld_wait();
-                const uint32_t col0 = n_base + c * 32;
-                if (row < s.M && col0 < s.N) {
-                    const uint32_t ncols = min(32u, s.N - col0);  // multiple of 8 (checked on host)
-                    if constexpr (kEpi == Epi::GatedGeluF16) {
+                for (uint32_t c = 0; c < kBlockN / 32; ++c) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+                    ptx::tmem_ld_wait();
+                    const uint32_t col0 = n_base + c * 32;
+                    if (row < s.M && col0 < s.N && !(s.idesc_extra >> 31)) {
+                        const uint32_t ncols = min(32u, s.N - col0);  // multiple of 16 (checked on host)
                         __half* crow = reinterpret_cast<__half*>(Cptr) + static_cast<size_t>(row) * s.ldc + (col0 >> 1);
 #pragma unroll
                         for (uint32_t j = 0; j < 2; ++j) {
@@ -218,51 +240,60 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                 *reinterpret_cast<uint4*>(crow + j * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             }
                         }
-                    } else if constexpr (kEpi == Epi::StoreF16 || kEpi == Epi::StoreF16Relu) {
-                        __half* crow = reinterpret_cast<__half*>(Cptr) + static_cast<size_t>(row) * s.ldc + col0;
+                    }
+                }
+                release_accumulator();
+            } else {
+                constexpr uint32_t kColsPerStore = kF16Out ? 64 : 32;  // 128 bytes per row either way
+                constexpr uint32_t kChunks = kBlockN / kColsPerStore;
+#pragma unroll 1
+                for (uint32_t c = 0; c < kChunks; ++c) {
+                    uint32_t pk[32];  // the 128 bytes of this lane's row
+                    if constexpr (kF16Out) {
+                        uint32_t v0[32], v1[32];
+                        ptx::tmem_ld_32x32b_x32(taddr + c * 64, v0);
+                        ptx::tmem_ld_32x32b_x32(taddr + c * 64 + 32, v1);
+                        ptx::tmem_ld_wait();
 #pragma unroll
-                        for (uint32_t j = 0; j < 4; ++j) {
-                            if (j * 8 < ncols) {
-                                uint32_t pk[4];
-#pragma unroll
-                                for (uint32_t q = 0; q < 4; ++q) {
-                                    float x0 = __uint_as_float(v[j * 8 + 2 * q]);
-                                    float x1 = __uint_as_float(v[j * 8 + 2 * q + 1]);
-                                    if constexpr (kEpi == Epi::StoreF16Relu) {
-                                        x0 = fmaxf(x0, 0.f);
-                                        x1 = fmaxf(x1, 0.f);
-                                    }
-                                    __half2 h = __floats2half2_rn(x0, x1);
-                                    pk[q] = *reinterpret_cast<uint32_t*>(&h);
-                                }
-                                *reinterpret_cast<uint4*>(crow + j * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        for (uint32_t i = 0; i < 16; ++i) {
+                            float a0 = __uint_as_float(v0[2 * i]), a1 = __uint_as_float(v0[2 * i + 1]);
+                            float b0 = __uint_as_float(v1[2 * i]), b1 = __uint_as_float(v1[2 * i + 1]);
+                            if constexpr (kEpi == Epi::StoreF16Relu) {
+                                a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f);
+                                b0 = fmaxf(b0, 0.f); b1 = fmaxf(b1, 0.f);
                             }
+                            __half2 ha = __floats2half2_rn(a0, a1), hb = __floats2half2_rn(b0, b1);
+                            pk[i] = *reinterpret_cast<uint32_t*>(&ha);
+                            pk[16 + i] = *reinterpret_cast<uint32_t*>(&hb);
                         }
                     } else {
-                        float* crow = reinterpret_cast<float*>(Cptr) + static_cast<size_t>(row) * s.ldc + col0;
+                        ptx::tmem_ld_32x32b_x32(taddr + c * 32, pk);
+                        ptx::tmem_ld_wait();
+                    }
+                    if (c + 1 == kChunks) release_accumulator();
+                    const uint32_t col0 = n_base + c * kColsPerStore;
+                    if (row0 < s.M && col0 < s.N && !(s.idesc_extra >> 31)) {  // warp-uniform
+                        if (lane == 0) ptx::bulk_wait_read<1>();  // the store that last used this buffer has read it
+                        __syncwarp();
+                        const uint32_t dst = ptx::smem_u32(stage_base + sbuf * 4096) + lane * 128;
 #pragma unroll
-                        for (uint32_t j = 0; j < 8; ++j) {
-                            if (j * 4 < ncols) {
-                                float4 x = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                                if constexpr (kEpi == Epi::AddF32) {
-                                    const float4 o = *reinterpret_cast<const float4*>(crow + j * 4);
-                                    x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
-                                }
-                                *reinterpret_cast<float4*>(crow + j * 4) = x;
-                            }
+                        for (uint32_t q = 0; q < 8; ++q)
+                            ptx::sts_v4(dst + ((q ^ (lane & 7u)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                        ptx::fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if constexpr (kEpi == Epi::AddF32)
+                                ptx::tma_reduce_add_2d(&tma_c, stage_base + sbuf * 4096, int32_t(col0), int32_t(row0));
+                            else
+                                ptx::tma_store_2d(&tma_c, stage_base + sbuf * 4096, int32_t(col0), int32_t(row0));
+                            ptx::bulk_commit();
                         }
+                        sbuf ^= 1;
                     }
                 }
             }
-            // accumulator stage drained: hand it back to the MMA issuer of the leader CTA
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if constexpr (kCtaGroup == 1) ptx::mbar_arrive(&tmem_empty_bar[as]);
-                else ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
-            }
         }
+        if (lane == 0) ptx::bulk_wait<0>();  // all stores of this warp have completed before the CTA retires
     }
 
     ptx::tc_fence_before();
