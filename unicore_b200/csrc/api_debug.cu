@@ -3,6 +3,8 @@
 // same launchers the product path uses, with host buffers in and out.
 #include <cuda_fp16.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "common.h"

@@ -4,7 +4,9 @@
 // Persistent kernel, two CTAs per SM (256 of the 512 TMEM columns each), 192 threads per CTA:
 //   warps 0-3  softmax: thread r owns query row r of the 128-row tile (TMEM lane r): tcgen05.ld of
 //              S, bias + mask + running max in the log2 domain, exp2, fp16 P written BACK INTO TMEM over
-//              the S columns (tcgen05.st), lazy rescale of the O accumulator, final O/l -> global
+//              the S columns (tcgen05.st), lazy rescale of the O accumulator, final O/l -> global.
+//              The first tile's row maximum gets 2^6 of head room, so the lazy rescale of O (needed only when a
+//              later score exceeds the reference by 2^8) almost never fires
 //   warp 4     TMA producer: Q (128 x 128), then K and V in 64-key tiles through two 2-stage rings
 //   warp 5     MMA issuer (one thread): S = Q.K^T (UMMA 128x64x16, both operands from 128B-swizzled
 //              smem) and O += P.V (UMMA 128x128x16, A = P from TMEM, B = V MN-major from smem)
@@ -37,6 +39,8 @@ constexpr uint32_t kSmemDynamic = kSmemTotal + 1024;  // slack for manual 1024 B
 constexpr uint32_t kTmemCols = 256;                   // O: [0,128)  S/P buffer 0: [128,192)  buffer 1: [192,256)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays below 2^8 between rescales
+constexpr float kHeadRoom = 6.0f;          // log2 units added to the first tile's row max: P starts at <= 2^-6 and
+                                           // rescales of the accumulator become rare (they were 23 % of the tiles)
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
@@ -216,8 +220,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         int cur_h = -1;
         uint32_t es = e_smem;
         float e_lo = 0.f, e_hi = 0.f;
+        Item nxt = get_item(blockIdx.x, n_work, work);  // grid <= n_items
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
-            const Item it = get_item(item, n_work, work);
+            const Item it = nxt;
+            if (item + gridDim.x < n_items) nxt = get_item(item + gridDim.x, n_work, work);  // prefetch the next record
             if (it.h != cur_h) {
                 // other warps may still read the current table: write the other buffer, then meet
                 cur_h = it.h;
@@ -231,11 +237,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             }
             const int row_seq = it.q0 + int(r);
             float m = -INFINITY, l = 0.f;
+            const bool warp_valid = it.q0 + int(warp * 32) < it.T;
             for (uint32_t j = 0; j < it.nt; ++j, ++g) {
                 const uint32_t b = g & 1, ph = (g >> 1) & 1;
                 const int j0 = int(j * kBN);
                 ptx::mbar_wait(&s_full[b], ph);
                 ptx::tc_fence_after();
+                uint32_t pk[32];
+                if (!warp_valid) {  // all 32 query rows lie past the end of the sequence: keep the protocol going only
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) pk[c] = 0u;
+                } else {
                 uint32_t v0[32], v1[32];
                 ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN, v0);
                 ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN + 32, v1);
@@ -273,10 +285,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 }
                 const float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
                 if (j == 0) {
-                    m = mx;  // key 0 is always valid, so mx is finite
+                    m = mx + kHeadRoom;  // key 0 is always valid, so mx is finite
                 } else if (__any_sync(0xffffffffu, mx > m + kRescaleThreshold)) {
                     // rescale the O accumulator of this warp's 32 rows (rare after the first tiles)
-                    const float m_new = fmaxf(m, mx);
+                    const float m_new = fmaxf(m, mx + kHeadRoom);
                     const float alpha = ex2(m - m_new);
                     m = m_new;
                     l *= alpha;
@@ -293,7 +305,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     }
                     ptx::tmem_st_wait();
                 }
-                uint32_t pk[32];
                 float sa = 0.f, sb = 0.f, sc = 0.f, sd = 0.f;
 #pragma unroll
                 for (int c = 0; c < 32; c += 2) {
@@ -304,6 +315,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     pk[c + 1] = pack_h2(p2, p3);
                 }
                 l += (sa + sb) + (sc + sd);
+                }
                 ptx::tmem_st_32x32b_x32(t_lane + 128 + b * kBN, pk);  // P over the first 32 columns of S
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();

@@ -130,7 +130,7 @@ void init_variant() {
 // Per-device one-time setup (function attributes are per device): call with the device current.
 void gemm_init_device() {
     init_variant<1, 256, 4>();
-    init_variant<2, 256, 5>();
+    init_variant<2, 256, 6>();
 
 }
 
@@ -162,7 +162,7 @@ void gemm_launch(cudaStream_t stream, int num_sms, int variant, Epi epi, const C
     if (M == 0 || N == 0) return;
     switch (variant) {
         case 0: launch_epi<1, 256, 4>(stream, num_sms, epi, tma_a, tma_b, C, s); break;
-        case 1: launch_epi<2, 256, 5>(stream, num_sms, epi, tma_a, tma_b, C, s); break;
+        case 1: launch_epi<2, 256, 6>(stream, num_sms, epi, tma_a, tma_b, C, s); break;
 
         default: throw Error(P5_ERR_ARG, strf("unknown GEMM variant %d", variant));
     }

@@ -11,9 +11,10 @@ namespace p5 {
 namespace ptx {
 
 #ifndef P5_MBAR_SPIN_LIMIT
-// A wait that never completes turns into a trap (reported as a launch failure) instead of a hung
-// GPU.  2^28 failed probes is several seconds; normal waits complete in < 10^3 probes.
-#define P5_MBAR_SPIN_LIMIT (1u << 28)
+// A wait that never completes turns into a trap (reported as a launch failure) instead of a hung GPU:
+// after this many failed probes a wall-clock watchdog starts, and P5_MBAR_TIMEOUT_NS later the kernel traps.
+#define P5_MBAR_SPIN_LIMIT 4096u
+#define P5_MBAR_TIMEOUT_NS 4000000000ull
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -68,26 +69,36 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// One probe of the barrier phase.  The suspend-time hint lets the hardware park the thread until the phase
+// completes (or the hint expires) instead of burning issue slots in a polling loop: the single-thread TMA and
+// MMA roles otherwise take a large share of their scheduler's slots away from the warps doing real work.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins >= P5_MBAR_SPIN_LIMIT) {
-            printf("p5: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x,
-                   (int)threadIdx.x, smem_u32(bar), parity);
-            __trap();
+        if (++spins >= P5_MBAR_SPIN_LIMIT) {  // slow path: start a wall-clock watchdog
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) {
+                t0 = now;
+            } else if (now - t0 > P5_MBAR_TIMEOUT_NS) {
+                printf("p5: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x,
+                       (int)threadIdx.x, smem_u32(bar), parity);
+                __trap();
+            }
         }
     }
 }
@@ -299,6 +310,14 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
         "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
         "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
         "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() {
