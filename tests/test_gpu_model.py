@@ -52,7 +52,7 @@ def test_model_info_and_tables(tiny, tiny_oracle):
         np.testing.assert_array_equal(tiny.bias_table(h), rel[buckets, h])
 
 
-@pytest.mark.parametrize("L", [1, 2, 17, 62, 63, 64, 65, 127, 350, 1030])
+@pytest.mark.parametrize("L", [1, 2, 17, 62, 63, 64, 65, 127, 128, 129, 350, 1030, 4000])
 def test_tiny_matches_oracle(tiny, tiny_oracle, L):
     rng = np.random.default_rng(L)
     _check_against_oracle(tiny, tiny_oracle, random_protein(rng, L), TINY_HID_TOL, TINY_LOGIT_TOL)
