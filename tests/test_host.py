@@ -196,3 +196,46 @@ def test_custom_lookup_all_found_needs_no_gpu(tmp_path, tiny_dir):
     assert (out.parent / "createdb.chk").read_text() == "1"
     p = _run([UNICORE, "createdb", str(inp), str(tmp_path / "o2" / "db"), tiny_dir, "--custom-lookup", str(tmp_path / "nodb")])
     assert p.returncode == 1 and "Custom lookup database does not exist" in p.stderr
+
+
+def test_genefasta_matches_reference_consumer(tmp_path):
+    """Tree-side consumer [REF src/seq/create_gene_specific_fasta.rs:27-88; src/modules/tree.rs:57-110]."""
+    db = str(tmp_path / "db")
+    entries = [("unicore_aaaaaaaaaa", "MKTAYIAKQR", "DVLVVVLCVV"), ("unicore_bbbbbbbbbb", "GGGGG", "PPPPP"),
+               ("unicore_cccccccccc", "ACDEFGHIK", "DDDLLLVVV")]
+    for suffix, col in (("_h", 0), ("", 1), ("_ss", 2)):
+        with open(db + suffix, "wb") as f:
+            for e in entries:
+                f.write(e[col].encode() + b"\n\0")
+    prof = tmp_path / "profile"
+    prof.mkdir()
+    (prof / "gene1.txt").write_text("unicore_aaaaaaaaaa SpA\nunicore_cccccccccc\tSpB\n")
+    (prof / "gene.2.txt").write_text("unicore_bbbbbbbbbb SpA\n")
+    (prof / "notes.md").write_text("ignored")
+    out = tmp_path / "tree"
+    p = _run([UNICORE, "genefasta", db, str(prof), str(out), "--db"])
+    assert p.returncode == 0, p.stderr
+    want = H.create_gene_specific_fasta(db, str(out / "fasta"), sorted(str(x) for x in prof.glob("*.txt")))
+    assert set(want) == {"gene1", "gene.2"}
+    for gene, (aa_txt, di_txt) in want.items():
+        assert (out / "fasta" / gene / "aa.fasta").read_text() == aa_txt
+        assert (out / "fasta" / gene / "3di.fasta").read_text() == di_txt
+        gdb = str(out / "fasta" / gene / f"{gene}_db")
+        assert H.read_db(gdb) == [l for l in aa_txt.splitlines() if not l.startswith(">")]
+        assert H.read_db(gdb + "_ss") == [l for l in di_txt.splitlines() if not l.startswith(">")]
+        assert H.read_db(gdb + "_h") == [l[1:] for l in aa_txt.splitlines() if l.startswith(">")]
+    (prof / "bad.txt").write_text("only_one_column\n")
+    p = _run([UNICORE, "genefasta", db, str(prof), str(tmp_path / "t2")])
+    assert p.returncode == 1 and "Invalid line in gene mapping file" in p.stderr
+
+
+def test_shim_base_createdb(tmp_path):
+    fasta = tmp_path / "aa.fasta"
+    fasta.write_text(">SpA desc\nMKTAYIAKQR\nQIS\n>SpB\nGGGGG\n")
+    db = str(tmp_path / "gene_db")
+    env = {k: v for k, v in os.environ.items() if k != "UNICORE_B200_REAL_FOLDSEEK"}
+    p = _run([SHIM, "base:createdb", str(fasta), db, "--shuffle", "0", "-v", "2"], env=env)
+    assert p.returncode == 0, p.stderr
+    assert H.read_db(db) == ["MKTAYIAKQRQIS", "GGGGG"] and H.read_db(db + "_h") == ["SpA desc", "SpB"]
+    assert int.from_bytes(open(db + ".dbtype", "rb").read(), "little") == 0
+    assert open(db + ".lookup").read() == "0\tSpA\t0\n1\tSpB\t0\n"

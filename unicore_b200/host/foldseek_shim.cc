@@ -34,6 +34,20 @@ int main(int argc, char** argv) {
     if (verb == "version") { puts("foldseek-b200 0.1.0"); return 0; }
     bool prostt5 = false;
     for (int i = 2; i < argc; ++i) prostt5 |= !strcmp(argv[i], "--prostt5-model");
+    if (verb == "base:createdb" && !getenv("UNICORE_B200_REAL_FOLDSEEK")) {
+        // `foldseek base:createdb <fasta> <db> --shuffle 0 -v V` of `unicore tree` [REF src/modules/tree.rs:87-105]:
+        // plain sequence DB, answered natively when no real foldseek is configured
+        std::vector<std::string> pos;
+        for (int i = 2; i < argc; ++i) {
+            const std::string a = argv[i];
+            if (a == "--shuffle" || a == "-v" || a == "--threads" || a == "--dbtype" || a == "--compressed") ++i;
+            else if (!a.empty() && a[0] == '-') { fprintf(stderr, "foldseek-b200: unknown option %s\n", a.c_str()); return 1; }
+            else pos.push_back(a);
+        }
+        if (pos.size() != 2 || !is_file(pos[0])) { fputs("foldseek-b200: base:createdb needs <fasta> <db>\n", stderr); return 1; }
+        write_sequence_db(pos[1], read_fasta_records(pos[0]), base_name(pos[0]));
+        return 0;
+    }
     if (verb != "createdb" || !prostt5) return passthrough(argv);
     std::vector<std::string> pos;
     std::string model;

@@ -84,6 +84,19 @@ void mkdir_p(const std::string& p) {
     if (mkdir(p.c_str(), 0777) != 0 && !is_dir(p)) die(ERR_GENERAL, "Could not create directory " + p);
 }
 
+std::vector<std::string> list_files_with_ext(const std::string& dir, const std::string& ext) {
+    std::vector<std::string> files;
+    DIR* d = opendir(dir.c_str());
+    if (!d) die(ERR_GENERAL, "Could not read directory " + dir);
+    while (dirent* e = readdir(d)) {
+        const std::string full = dir + (dir.back() == '/' ? "" : "/") + e->d_name;
+        if (is_file(full) && extension(e->d_name) == ext) files.push_back(full);
+    }
+    closedir(d);
+    std::sort(files.begin(), files.end());
+    return files;
+}
+
 // Rust's BufRead::lines(): split at '\n', drop one trailing '\r'; lines that are not valid UTF-8 are
 // errors and are skipped by the reference's filter_map(|l| l.ok()).
 static bool valid_utf8(const std::string& s) {
@@ -304,6 +317,65 @@ void write_foldseek_db(const std::string& db, const std::vector<Record>& recs, c
     lookup.flush();
     source.flush();
     if (!lookup || !source) die(ERR_GENERAL, "Could not write lookup/source of " + db);
+}
+
+void write_sequence_db(const std::string& db, const std::vector<Record>& recs, const std::string& source_name) {
+    constexpr int32_t kAminoAcids = 0, kGeneric = 12;
+    write_one_db(db, recs.size(), kAminoAcids, [&](size_t i) -> const std::string& { return recs[i].seq; });
+    write_one_db(db + "_h", recs.size(), kGeneric, [&](size_t i) -> const std::string& { return recs[i].name; });
+    std::ofstream lookup(db + ".lookup", std::ios::binary);
+    for (size_t i = 0; i < recs.size(); ++i) {
+        const std::string& h = recs[i].name;
+        size_t e = 0;
+        while (e < h.size() && !isspace(static_cast<unsigned char>(h[e]))) ++e;
+        lookup << i << '\t' << h.substr(0, e) << '\t' << 0 << '\n';
+    }
+    std::ofstream source(db + ".source", std::ios::binary);
+    source << 0 << '\t' << source_name << '\n';
+    lookup.flush();
+    source.flush();
+    if (!lookup || !source) die(ERR_GENERAL, "Could not write lookup/source of " + db);
+}
+
+size_t create_gene_specific_fasta(const std::string& input_db, const std::string& gene_dir,
+                                  const std::vector<std::string>& gene_lists, bool with_db) {
+    const std::vector<std::string> names = read_db(input_db + "_h"), aa = read_db(input_db), ss = read_db(input_db + "_ss");
+    if (names.size() != aa.size() || names.size() != ss.size())
+        die(ERR_GENERAL, "Lengths of names, amino acid and 3di sequences in database are not same");
+    std::unordered_map<std::string, size_t> idx;
+    for (size_t i = 0; i < names.size(); ++i) idx[names[i]] = i;  // HashMap insert: a repeated name keeps the last entry
+    size_t cnt = 0;
+    for (const std::string& gene_path : gene_lists) {
+        const std::string gene = file_stem(gene_path);
+        const std::string out_dir = gene_dir + "/" + gene;
+        mkdir_p(out_dir);
+        std::vector<Record> aa_recs, ss_recs;
+        for_each_line(gene_path, [&](const std::string& line) {
+            if (!valid_utf8(line)) return;
+            std::vector<std::string> parts;  // split_whitespace()
+            size_t i = 0;
+            while (i < line.size()) {
+                while (i < line.size() && isspace(static_cast<unsigned char>(line[i]))) ++i;
+                size_t j = i;
+                while (j < line.size() && !isspace(static_cast<unsigned char>(line[j]))) ++j;
+                if (j > i) parts.push_back(line.substr(i, j - i));
+                i = j;
+            }
+            if (parts.size() != 2) die(ERR_GENERAL, "Invalid line in gene mapping file: " + line);
+            auto it = idx.find(parts[0]);
+            if (it == idx.end()) die(ERR_GENERAL, "Sequence " + parts[1] + " not found in the database");
+            aa_recs.push_back({parts[1], aa[it->second]});
+            ss_recs.push_back({parts[1], ss[it->second]});
+        });
+        write_fasta(out_dir + "/aa.fasta", aa_recs);
+        write_fasta(out_dir + "/3di.fasta", ss_recs);
+        if (with_db) {
+            write_sequence_db(out_dir + "/" + gene + "_db", aa_recs, "aa.fasta");
+            write_sequence_db(out_dir + "/" + gene + "_db_ss", ss_recs, "3di.fasta");
+        }
+        ++cnt;
+    }
+    return cnt;
 }
 
 std::vector<std::string> read_db(const std::string& path) {

@@ -60,6 +60,17 @@ std::vector<std::string> read_db(const std::string& path);
 void split_by_lookup(const std::string& lookup_db, std::vector<Record>& recs, std::vector<Record>& found,
                      std::vector<std::string>& found_ss);
 
+// Sequence DB without a 3Di companion: <db>, <db>_h (+ .index, .dbtype, .lookup, .source) — what
+// `foldseek base:createdb <fasta> <db> --shuffle 0` writes for the per-gene FASTA files of `unicore tree`
+// [REF src/modules/tree.rs:78-110].
+void write_sequence_db(const std::string& db, const std::vector<Record>& recs, const std::string& source_name);
+
+// [REF src/seq/create_gene_specific_fasta.rs:27-88] for every gene list file (lines "<db name> <label>") writes
+// <gene_dir>/<gene>/aa.fasta and 3di.fasta from the DB triple; with_db additionally writes the per-gene
+// Foldseek DBs <gene>_db and <gene>_db_ss natively.  Returns the number of genes.
+size_t create_gene_specific_fasta(const std::string& input_db, const std::string& gene_dir,
+                                  const std::vector<std::string>& gene_lists, bool with_db);
+
 // [REF src/util/checkpoint.rs:2-10]
 void write_checkpoint(const std::string& path, const std::string& content);
 std::string read_checkpoint(const std::string& path);
@@ -71,6 +82,7 @@ std::string parent_dir(const std::string& p);  // Rust Path::parent(): "" for a 
 std::string file_stem(const std::string& p);
 std::string base_name(const std::string& p);
 void mkdir_p(const std::string& p);
+std::vector<std::string> list_files_with_ext(const std::string& dir, const std::string& ext);  // sorted
 
 // runs the predictor over the records: returns one 3Di string per record (calls the C ABI)
 struct PredictOptions {

@@ -123,6 +123,21 @@ int main(int argc, char** argv) {
     }
     const std::string verb = argv[1];
     if (verb == "version") { puts("unicore-b200 0.1.0 (unicore v1.1.1 createdb contract)"); return 0; }
+    if (verb == "genefasta") {
+        // tree-side consumer of the DB [REF src/modules/tree.rs:57-110]: unicore-b200 genefasta <db> <profile_dir> <out_dir> [--db]
+        std::vector<std::string> pos;
+        bool with_db = false;
+        for (int i = 2; i < argc; ++i) {
+            if (!strcmp(argv[i], "--db")) with_db = true;
+            else if (!strcmp(argv[i], "-v") && i + 1 < argc) g_verbosity = atoi(argv[++i]);
+            else pos.push_back(argv[i]);
+        }
+        if (pos.size() != 3) die(ERR_ARGPARSE, "genefasta <db> <profile_dir> <out_dir> [--db]");
+        std::vector<std::string> lists = list_files_with_ext(pos[1], "txt");
+        const size_t n = create_gene_specific_fasta(pos[0], pos[2] + "/fasta", lists, with_db);
+        msg(3, "Gene specific fasta files prepared in: " + pos[2] + "/fasta (" + std::to_string(n) + " genes)");
+        return 0;
+    }
     if (verb == "createdb") {
         if (argc == 2) { fputs(kUsage, stdout); return ERR_ARGPARSE; }
         return createdb(argc - 2, argv + 2);
