@@ -152,10 +152,25 @@ def run_reference(args, rank, world):
                              "sample": f"{args.steps} steps x 1 sequence x 350 aa after {args.warmup} warm-up"},
             "e2e": {"value": v, "unit": "residues/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter) was moved to
+    stderr by main()."""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
+_REAL_STDOUT = sys.stdout
 
 
 def main():
+    global _REAL_STDOUT
+    # keep stdout clean for the JSON line: native libraries (NCCL prints its version) write to fd 1
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -288,7 +303,7 @@ def main():
                                 "sample": f"first {args.cpu_sample_seqs} sequences of config 2 ({res} residues, {dt:.1f} s), "
                                           "numpy oracle, one sequence at a time"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     pred.close()
     if world > 1:
         dist.destroy_process_group()
