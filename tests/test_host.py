@@ -239,3 +239,35 @@ def test_shim_base_createdb(tmp_path):
     assert H.read_db(db) == ["MKTAYIAKQRQIS", "GGGGG"] and H.read_db(db + "_h") == ["SpA desc", "SpB"]
     assert int.from_bytes(open(db + ".dbtype", "rb").read(), "little") == 0
     assert open(db + ".lookup").read() == "0\tSpA\t0\n1\tSpB\t0\n"
+
+
+# ---- property tests: the C++ host functions agree with the restated Rust on arbitrary inputs ----
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_HEADER_CHARS = st.characters(blacklist_categories=("Cs",), blacklist_characters="\n\r\0")
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.text(_HEADER_CHARS, max_size=60))
+def test_sanitize_header_property(hostlib, key):
+    assert _call(hostlib.ubh_sanitize_header, key.encode("utf-8")) == H.sanitize_header(key)
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.binary(max_size=300))
+def test_md5_property(hostlib, data):
+    assert _call(hostlib.ubh_md5_hex, data) == hashlib.md5(data).hexdigest()
+
+
+_LINE = st.one_of(
+    st.text(st.sampled_from("ACDEFGHIKLMNPQRSTVWYX acd*-"), max_size=30),
+    st.builds(lambda h: ">" + h, st.text(st.sampled_from("abcXYZ |=;:,()/_0123 \t"), max_size=20)),
+    st.just(""), st.just(">"))
+
+
+@settings(max_examples=120, deadline=None)
+@given(st.lists(_LINE, max_size=14), st.sampled_from(["\n", "\r\n"]), st.booleans())
+def test_read_fasta_property(hostlib, tmp_path_factory, lines, eol, trailing):
+    p = tmp_path_factory.mktemp("fa") / "x.fa"
+    p.write_bytes((eol.join(lines) + (eol if trailing and lines else "")).encode())
+    assert _read_fasta_cpp(hostlib, str(p)) == list(H.read_fasta(str(p)).items())
