@@ -271,3 +271,39 @@ def test_read_fasta_property(hostlib, tmp_path_factory, lines, eol, trailing):
     p = tmp_path_factory.mktemp("fa") / "x.fa"
     p.write_bytes((eol.join(lines) + (eol if trailing and lines else "")).encode())
     assert _read_fasta_cpp(hostlib, str(p)) == list(H.read_fasta(str(p)).items())
+
+
+def test_profile_matches_reference_logic(tmp_path):
+    """[REF src/modules/profile.rs:13-147] on a synthetic .map + cluster table."""
+    import random
+    rnd = random.Random(3)
+    species = [f"Sp{i}" for i in range(7)]
+    genes = [f"unicore_{i:010x}" for i in range(120)]
+    db = str(tmp_path / "db")
+    with open(db + ".map", "w") as f:
+        for g in genes:
+            for sp in rnd.sample(species, rnd.choice([1, 1, 1, 2])):
+                f.write(f"{g}\t{sp}\tsome_header_{g}\n")
+    tsv = tmp_path / "clust.tsv"
+    with open(tsv, "w") as f:
+        pool = genes[:]
+        rnd.shuffle(pool)
+        k = 0
+        while pool:
+            members = [pool.pop() for _ in range(min(len(pool), rnd.choice([1, 3, 6, 7, 8, 9])))]
+            rep = members[0] if k % 2 else f"x-{members[0]}-y"   # exercises query.split('-').nth(1)
+            k += 1
+            for m in members:
+                f.write(f"{rep}\t{m}\n")
+        f.write("orphan\tnot_in_map\n")
+    out = tmp_path / "prof"
+    for thr in (80, 30):
+        p = _run([UNICORE, "profile", db, str(tsv), str(out / str(thr)), "-t", str(thr)])
+        assert p.returncode == 0, p.stderr
+        cop, files, core, total = H.profile(str(tsv), db + ".map", thr)
+        assert (out / str(thr) / "copiness.tsv").read_text() == cop
+        got = {x.stem: sorted(x.read_text().splitlines()) for x in (out / str(thr)).glob("*.txt")}
+        assert got == files and len(files) <= core
+        assert f"{core} structural core genes found from {total} candidates" in p.stdout
+        assert (out / str(thr) / "profile.chk").read_text() == "1"
+    assert _run([UNICORE, "profile", db]).returncode == 0x40

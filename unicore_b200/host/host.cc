@@ -5,11 +5,14 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <charconv>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <map>
+#include <set>
 #include <unordered_map>
 
 #include "md5.h"
@@ -416,6 +419,109 @@ void split_by_lookup(const std::string& lookup_db, std::vector<Record>& recs, st
         found.push_back(std::move(h.first));
         found_ss.push_back(std::move(h.second));
     }
+}
+
+static std::vector<std::string> split_ws(const std::string& line) {
+    std::vector<std::string> parts;
+    size_t i = 0;
+    while (i < line.size()) {
+        while (i < line.size() && isspace(static_cast<unsigned char>(line[i]))) ++i;
+        size_t j = i;
+        while (j < line.size() && !isspace(static_cast<unsigned char>(line[j]))) ++j;
+        if (j > i) parts.push_back(line.substr(i, j - i));
+        i = j;
+    }
+    return parts;
+}
+
+// Rust's `{}` for f64: shortest decimal that round-trips, no exponent in this range, no trailing ".0"
+static std::string rust_f64(double x) {
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof(buf), x);
+    return std::string(buf, r.ptr);
+}
+
+std::pair<size_t, size_t> profile_clusters(const std::string& tsv, const std::string& mapping, const std::string& out_dir,
+                                           size_t threshold, bool print_copiness) {
+    std::unordered_map<std::string, std::set<std::string>> gene_to_spe;
+    std::set<std::string> species;
+    for_each_line(mapping, [&](const std::string& line) {
+        if (!valid_utf8(line)) return;
+        const auto parts = split_ws(line);
+        if (parts.size() < 2) die(ERR_GENERAL, "Invalid line in mapping file: " + line);
+        gene_to_spe[parts[0]].insert(parts[1]);
+        species.insert(parts[1]);
+    });
+    const size_t species_count = species.size();
+    std::ofstream cop;
+    if (print_copiness) {
+        cop.open(out_dir + "/copiness.tsv", std::ios::binary);
+        if (!cop) die(ERR_GENERAL, "Could not create " + out_dir + "/copiness.tsv");
+        cop << "Query\tMultipleCopyPercent\tSingleCopyPercent\n";
+    }
+    std::map<std::string, int> spe_cnt;
+    std::map<std::string, std::set<std::string>> gene2spe;
+    std::map<std::string, size_t> spe_full_cnt;
+    for (const auto& s : species) spe_full_cnt[s] = 0;
+    size_t total = 0, core = 0;
+    bool have = false;
+    std::string cur;
+    auto flush_query = [&] {
+        ++total;
+        size_t single = 0;
+        for (const auto& kv : spe_cnt) single += kv.second == 1;
+        const double sp = double(single) * 100.0 / double(species_count), mp = double(spe_cnt.size()) * 100.0 / double(species_count);
+        if (g_verbosity >= 4) {
+            char b[256];
+            snprintf(b, sizeof(b), "Gene %s reported %.2f%% single copy and %.2f%% multiple copy", cur.c_str(), sp, mp);
+            msg(4, b);
+        }
+        if (print_copiness) cop << cur << '\t' << rust_f64(mp) << '\t' << rust_f64(sp) << '\n';
+        if (single * 100 >= threshold * species_count) {
+            std::string name = cur;  // query.split('-').nth(1).unwrap_or(query)
+            const size_t a = cur.find('-');
+            if (a != std::string::npos) {
+                const size_t b = cur.find('-', a + 1);
+                name = cur.substr(a + 1, b == std::string::npos ? std::string::npos : b - a - 1);
+            }
+            std::ofstream out(out_dir + "/" + name + ".txt", std::ios::binary);
+            if (!out) die(ERR_GENERAL, "Could not create " + out_dir + "/" + name + ".txt");
+            for (const auto& kv : gene2spe)  // species-sorted (the reference iterates a HashMap: order unspecified)
+                if (kv.second.size() == 1) out << *kv.second.begin() << '\t' << kv.first << '\n';
+            ++core;
+            for (const auto& kv : spe_cnt)
+                if (kv.second == 1) {
+                    auto it = spe_full_cnt.find(kv.first);
+                    if (it == spe_full_cnt.end()) die(ERR_GENERAL, "Species " + kv.first + " not found in the mapping file");
+                    ++it->second;
+                }
+        }
+    };
+    for_each_line(tsv, [&](const std::string& line) {
+        if (!valid_utf8(line)) return;
+        const auto parts = split_ws(line);
+        if (parts.size() < 2) die(ERR_GENERAL, "Invalid line in tsv file: " + line);
+        if (!have || parts[0] != cur) {
+            if (have) flush_query();
+            cur = parts[0];
+            have = true;
+            spe_cnt.clear();
+            gene2spe.clear();
+        }
+        auto it = gene_to_spe.find(parts[1]);
+        if (it != gene_to_spe.end())
+            for (const auto& spe : it->second) {
+                ++spe_cnt[spe];
+                gene2spe[spe].insert(parts[1]);
+            }
+    });
+    if (have) flush_query();
+    msg(3, std::to_string(core) + " structural core genes found from " + std::to_string(total) + " candidates");
+    const size_t core_threshold = (core + 1) / 2;
+    for (const auto& kv : spe_full_cnt)
+        if (kv.second < core_threshold && g_verbosity >= 2)
+            fprintf(stderr, "Warning: Species %s has only %zu core genes out of %zu core genes\n", kv.first.c_str(), kv.second, core);
+    return {core, total};
 }
 
 void write_checkpoint(const std::string& path, const std::string& content) {

@@ -71,6 +71,13 @@ void write_sequence_db(const std::string& db, const std::vector<Record>& recs, c
 size_t create_gene_specific_fasta(const std::string& input_db, const std::string& gene_dir,
                                   const std::vector<std::string>& gene_lists, bool with_db);
 
+// [REF src/modules/profile.rs:13-147] taxonomic profile of the clusters: `mapping` is createdb's .map (gene ->
+// species), `tsv` the cluster/search table (query, target per line, grouped by query).  Writes copiness.tsv
+// (optional) and one <gene>.txt per structural core gene (single-copy in >= threshold % of the species).
+// Returns (core genes, candidates).
+std::pair<size_t, size_t> profile_clusters(const std::string& tsv, const std::string& mapping, const std::string& out_dir,
+                                           size_t threshold, bool print_copiness);
+
 // [REF src/util/checkpoint.rs:2-10]
 void write_checkpoint(const std::string& path, const std::string& content);
 std::string read_checkpoint(const std::string& path);

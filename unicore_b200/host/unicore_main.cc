@@ -117,12 +117,40 @@ static int createdb(int argc, char** argv) {
 
 int main(int argc, char** argv) {
     if (argc < 2 || !strcmp(argv[1], "help") || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) {
-        fputs("unicore-b200: B200-native `unicore createdb`\n\nCommands:\n  createdb  Create Foldseek database from amino acid sequences\n  version   Print version\n\n", stdout);
+        fputs("unicore-b200: B200-native `unicore createdb`\n\nCommands:\n  createdb   Create Foldseek database from amino acid sequences\n"
+              "  profile    Taxonomic profiling of the clusters: core structures (reference `unicore profile`)\n"
+              "  genefasta  Per-gene aa/3Di FASTA (+ DBs) from a database and a profile directory (first step of `unicore tree`)\n"
+              "  version    Print version\n\n", stdout);
         fputs(kUsage, stdout);
         return argc < 2 ? ERR_ARGPARSE : 0;
     }
     const std::string verb = argv[1];
     if (verb == "version") { puts("unicore-b200 0.1.0 (unicore v1.1.1 createdb contract)"); return 0; }
+    if (verb == "profile") {
+        // [REF src/util/arg_parser.rs:274-293; src/modules/profile.rs:149-171]
+        std::vector<std::string> pos;
+        size_t threshold = 80;
+        bool copiness = true;
+        for (int i = 2; i < argc; ++i) {
+            const std::string a = argv[i];
+            if ((a == "-t" || a == "--threshold") && i + 1 < argc) {
+                const long t = atol(argv[++i]);
+                if (t < 0 || t > 100) die(ERR_ARGPARSE, "profile - threshold must be in 0..100");
+                threshold = size_t(t);
+            } else if ((a == "-p" || a == "--print-copiness") && i + 1 < argc) copiness = std::string(argv[++i]) != "false";
+            else if (a == "--threads" && i + 1 < argc) ++i;
+            else if ((a == "-v" || a == "--verbosity") && i + 1 < argc) g_verbosity = atoi(argv[++i]);
+            else pos.push_back(a);
+        }
+        if (pos.size() < 1) die(ERR_ARGPARSE, "profile - input");
+        if (pos.size() < 2) die(ERR_ARGPARSE, "profile - mapping");
+        if (pos.size() < 3) die(ERR_ARGPARSE, "profile - output");
+        mkdir_p(pos[2]);
+        write_checkpoint(pos[2] + "/profile.chk", "0");
+        profile_clusters(pos[1], pos[0] + ".map", pos[2], threshold, copiness);
+        write_checkpoint(pos[2] + "/profile.chk", "1");
+        return 0;
+    }
     if (verb == "genefasta") {
         // tree-side consumer of the DB [REF src/modules/tree.rs:57-110]: unicore-b200 genefasta <db> <profile_dir> <out_dir> [--db]
         std::vector<std::string> pos;
