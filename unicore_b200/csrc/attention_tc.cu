@@ -15,6 +15,8 @@
 // Work item = (sequence, 128-query tile, head); items are dealt round-robin to the persistent CTAs.
 #include "kernels.h"
 
+#include <cstdlib>
+
 #include "common.h"
 #include "gemm_launch.h"
 #include "ptx.cuh"
@@ -391,7 +393,8 @@ void launch_attention_tc(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, 
                "relative attention max distance %u: the tcgen05 attention kernel assumes <= 128", max_dist);
     const uint64_t n_items = uint64_t(n_work) * H;
     P5_REQUIRE(n_items < (1ull << 31), P5_ERR_UNSUPPORTED, "too many attention work items");
-    const uint32_t grid = uint32_t(std::min<uint64_t>(n_items, uint64_t(2 * num_sms)));
+    static const int ctas_per_sm = getenv("P5_ATTN_CTAS") ? atoi(getenv("P5_ATTN_CTAS")) : 2;  // experiment knob
+    const uint32_t grid = uint32_t(std::min<uint64_t>(n_items, uint64_t(ctas_per_sm * num_sms)));
     attention_tc_kernel<<<grid, kThreads, kSmemDynamic, st>>>(tm_q, tm_kv, ctx, work128, n_work, uint32_t(n_items), H, e_ext);
     P5_CUDA(cudaGetLastError());
 }
