@@ -92,3 +92,29 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cc", ".h", ".cuh", ".cpp")):
                 src = open(os.path.join(dp, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_cnn_head_found_by_shape(tmp_path):
+    """Unknown CNN tensor names: the loader falls back to detection by shape.  On CPU the load
+    must get past the format checks and stop only at the device requirement."""
+    import torch
+    w = synth.make_weights(spec.TINY, 7)
+    renamed = {}
+    for k, v in w.items():
+        k2 = k.replace("cnn.conv0.", "head.layer_a.").replace("cnn.conv1.", "head.layer_b.")
+        renamed[k2] = v
+    d = tmp_path / "m"
+    d.mkdir()
+    gguf_io.write_gguf(str(d / spec.WEIGHT_FILE), spec.metadata(spec.TINY), renamed)
+    rc, msg = _load(str(d))
+    if torch.cuda.is_available():
+        assert rc == 0, msg
+    else:
+        assert rc == 4 and "no CPU fallback" in msg, msg
+    # a file without any head is a format error
+    nohead = {k: v for k, v in w.items() if not k.startswith("cnn.")}
+    d2 = tmp_path / "m2"
+    d2.mkdir()
+    gguf_io.write_gguf(str(d2 / spec.WEIGHT_FILE), spec.metadata(spec.TINY), nohead)
+    rc, msg = _load(str(d2))
+    assert rc == 3 and "CNN head" in msg

@@ -239,3 +239,17 @@ def test_in_process_multi_device(tiny_dir):
         out = np.zeros(len(aa), np.uint8)
         p.run_staged(out)
         np.testing.assert_array_equal(out, want)
+
+
+def test_cnn_head_detected_by_shape_gives_same_letters(tmp_path, tiny):
+    """A gguf whose CNN tensors carry unknown names predicts exactly what the canonical file does."""
+    from unicore_b200 import gguf_io, synth
+    w = synth.make_weights(spec.TINY, 7)
+    renamed = {k.replace("cnn.conv0.", "head.layer_a.").replace("cnn.conv1.", "head.layer_b."): v for k, v in w.items()}
+    d = tmp_path / "renamed"
+    d.mkdir()
+    gguf_io.write_gguf(str(d / spec.WEIGHT_FILE), spec.metadata(spec.TINY), renamed)
+    rng = np.random.default_rng(51)
+    seqs = [random_protein(rng, L) for L in (20, 130, 333)]
+    with Predictor(str(d)) as p:
+        assert p.predict(seqs) == tiny.predict(seqs)

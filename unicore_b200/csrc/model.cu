@@ -299,10 +299,37 @@ static const char* kCnnAliases[4][4] = {
     {"cnn.conv1.weight", "cnn.3.weight", "classifier.3.weight", "conv1.weight"},
     {"cnn.conv1.bias", "cnn.3.bias", "classifier.3.bias", "conv1.bias"},
 };
+// The CNN head's tensor names inside Foldseek's own gguf are not known here: known aliases first,
+// then detection by shape: conv0 = the 3-D tensor [C1, d_model, K], conv1 = the 3-D tensor [classes <= 20, C1, K],
+// biases = the 1-D tensors of C1 / classes elements whose name shares the weight's prefix.
 static const GgufTensor& cnn_tensor(const GgufFile& g, int which) {
     for (const char* n : kCnnAliases[which])
         if (g.has_tensor(n)) return g.tensor(n);
-    throw Error(P5_ERR_FORMAT, strf("%s: CNN head tensor %s (or an alias) is missing", g.path().c_str(), kCnnAliases[which][0]));
+    const uint64_t d_model = g.tensor("token_embd.weight").ne.at(0);
+    const GgufTensor *c0 = nullptr, *c1 = nullptr;
+    for (const auto& kv : g.tensors()) {
+        const GgufTensor& t = kv.second;
+        if (t.ne.size() != 3 || t.name.rfind("enc.", 0) == 0 || t.name.rfind("dec.", 0) == 0) continue;
+        if (t.ne[1] == d_model && !c0) c0 = &t;
+    }
+    if (c0)
+        for (const auto& kv : g.tensors()) {
+            const GgufTensor& t = kv.second;
+            if (t.ne.size() == 3 && &t != c0 && t.ne[1] == c0->ne[2] && t.ne[0] == c0->ne[0] && t.ne[2] <= 20 && !c1) c1 = &t;
+        }
+    auto bias_of = [&](const GgufTensor* w) -> const GgufTensor* {
+        if (!w) return nullptr;
+        const std::string stem = w->name.substr(0, w->name.rfind('.'));  // "...weight" -> prefix
+        for (const auto& kv : g.tensors()) {
+            const GgufTensor& t = kv.second;
+            if (t.ne.size() == 1 && t.ne[0] == w->ne[2] && t.name.rfind(stem, 0) == 0 && t.name != w->name) return &t;
+        }
+        return nullptr;
+    };
+    const GgufTensor* pick = which == 0 ? c0 : which == 2 ? c1 : bias_of(which == 1 ? c0 : c1);
+    if (pick) return *pick;
+    throw Error(P5_ERR_FORMAT, strf("%s: CNN head tensor %s (or an alias, or a tensor of the expected shape) is missing",
+                                    g.path().c_str(), kCnnAliases[which][0]));
 }
 
 void DeviceCtx::init(int device, const Model* m) {
