@@ -307,3 +307,24 @@ def test_profile_matches_reference_logic(tmp_path):
         assert f"{core} structural core genes found from {total} candidates" in p.stdout
         assert (out / str(thr) / "profile.chk").read_text() == "1"
     assert _run([UNICORE, "profile", db]).returncode == 0x40
+
+
+def test_afdb_lookup_with_local_tables(tmp_path, tiny_dir):
+    """[REF src/seq/afdb_lookup.rs:50-129] with the md5 tables present: key = md5(sequence + LF), table = its first byte."""
+    inp = _make_inputs(tmp_path / "in")
+    data, _ = H.collect(str(inp), max_len=200)
+    tables = tmp_path / "afdb" / "md5"
+    tables.mkdir(parents=True)
+    (tables / "00.tsv").write_text("00ffffffffffffffffffffffffffffff\tAAAA\n")
+    for aa in data.values():
+        h = hashlib.md5((aa + "\n").encode()).hexdigest()
+        with open(tables / f"{h[:2]}.tsv", "a") as f:
+            f.write(f"{h}\t{'V' * len(aa)}\textra\n")
+    out = tmp_path / "o" / "db"
+    p = _run([UNICORE, "createdb", str(inp), str(out), tiny_dir, "--max-len", "200", "--afdb-lookup", str(tmp_path / "afdb")])
+    assert p.returncode == 0, p.stderr
+    assert "2 sequences found from the lookup tables" in p.stdout
+    entries = H.check_foldseek_db(str(out))
+    assert all(ss == "V" * len(aa) and aa == data[n] for n, aa, ss in entries) and len(entries) == 2
+    p = _run([UNICORE, "createdb", str(inp), str(tmp_path / "o2" / "db"), tiny_dir, "--afdb-lookup", str(tmp_path / "none")])
+    assert p.returncode == 0x10 and "AFDB lookup tables not found" in p.stderr

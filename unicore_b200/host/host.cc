@@ -421,6 +421,58 @@ void split_by_lookup(const std::string& lookup_db, std::vector<Record>& recs, st
     }
 }
 
+void split_by_afdb(const std::string& dir, std::vector<Record>& recs, std::vector<Record>& found,
+                   std::vector<std::string>& found_ss) {
+    std::string md5_path = dir + "/md5";
+    if (is_file(dir + "/00.tsv")) md5_path = dir;
+    if (!is_file(md5_path + "/00.tsv"))
+        die(ERR_FILE_NOT_FOUND, md5_path + "/00.tsv: AFDB lookup tables not found (this build does not download them; fetch the "
+                                "256 md5 tables with the reference `unicore createdb --afdb-lookup` where a network exists)");
+    std::vector<std::vector<std::pair<size_t, std::string>>> split(256);  // table -> (record index, md5 hex)
+    for (size_t i = 0; i < recs.size(); ++i) {
+        Md5 m;
+        m.update(recs[i].seq.data(), recs[i].seq.size());
+        m.update("\n", 1);  // the tables hash the sequence with its line feed
+        const std::string hex = m.hex();
+        split[std::stoul(hex.substr(0, 2), nullptr, 16)].emplace_back(i, hex);
+    }
+    std::vector<char> hit(recs.size(), 0);
+    std::vector<std::string> hit_ss(recs.size());
+    static const char* dg = "0123456789abcdef";
+    for (int t = 0; t < 256; ++t) {
+        if (split[t].empty()) continue;
+        const std::string table = md5_path + "/" + dg[t >> 4] + dg[t & 15] + ".tsv";
+        std::unordered_map<std::string, std::string> map;
+        for_each_line(table, [&](const std::string& line) {
+            const size_t a = line.find('\t');
+            if (a == std::string::npos) return;
+            const size_t b = line.find('\t', a + 1);
+            map[line.substr(0, a)] = line.substr(a + 1, b == std::string::npos ? std::string::npos : b - a - 1);
+        });
+        for (const auto& e : split[t]) {
+            auto it = map.find(e.second);
+            if (it != map.end() && it->second.size() == recs[e.first].seq.size()) {
+                hit[e.first] = 1;
+                hit_ss[e.first] = it->second;
+            }
+        }
+    }
+    std::vector<Record> keep;
+    std::vector<std::pair<Record, std::string>> conv;
+    for (size_t i = 0; i < recs.size(); ++i) {
+        if (hit[i]) conv.emplace_back(std::move(recs[i]), std::move(hit_ss[i]));
+        else keep.push_back(std::move(recs[i]));
+    }
+    std::sort(conv.begin(), conv.end(), [](const auto& a, const auto& b) { return a.first.name < b.first.name; });
+    msg(3, std::to_string(conv.size()) + " sequences found from the lookup tables");
+    msg(3, std::to_string(keep.size()) + " sequences not found and will be predicted");
+    recs = std::move(keep);
+    for (auto& c : conv) {
+        found.push_back(std::move(c.first));
+        found_ss.push_back(std::move(c.second));
+    }
+}
+
 static std::vector<std::string> split_ws(const std::string& line) {
     std::vector<std::string> parts;
     size_t i = 0;

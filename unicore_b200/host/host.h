@@ -78,6 +78,12 @@ size_t create_gene_specific_fasta(const std::string& input_db, const std::string
 std::pair<size_t, size_t> profile_clusters(const std::string& tsv, const std::string& mapping, const std::string& out_dir,
                                            size_t threshold, bool print_copiness);
 
+// [REF src/seq/afdb_lookup.rs:50-129] run_afdb with the tables already on disk (`<dir>/md5/XX.tsv` or `<dir>/XX.tsv`,
+// lines "<md5 hex of sequence + LF>\t<3Di>"; XX = first byte of that md5).  This build has no network code: missing
+// tables are an error instead of a 30 GB download.  Same outputs as split_by_lookup.
+void split_by_afdb(const std::string& dir, std::vector<Record>& recs, std::vector<Record>& found,
+                   std::vector<std::string>& found_ss);
+
 // [REF src/util/checkpoint.rs:2-10]
 void write_checkpoint(const std::string& path, const std::string& content);
 std::string read_checkpoint(const std::string& path);

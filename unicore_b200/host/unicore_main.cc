@@ -23,7 +23,7 @@ static const char* kUsage =
     "  -o, --overwrite               Force overwrite output database\n"
     "      --max-len <MAX_LEN>       Set maximum sequence length threshold\n"
     "  -g, --gpu                     Accepted for compatibility (this build always runs on the GPU)\n"
-    "      --afdb-lookup <PATH>      Not implemented in this build (needs the 30 GB AFDB tables)\n"
+    "      --afdb-lookup <PATH>      Use AFDB lookup tables already on disk (<PATH>/md5/XX.tsv); no download in this build\n"
     "      --custom-lookup <PATH>    Use custom lookup database, accepts any Foldseek database to reference against\n"
     "      --threads <THREADS>       Accepted for compatibility [default: 0]\n"
     "  -v, --verbosity <VERBOSITY>   0: quiet, 1: +errors, 2: +warnings, 3: +info, 4: +debug [default: 3]\n"
@@ -74,7 +74,6 @@ static int createdb(int argc, char** argv) {
     const std::string input = pos[0], output = pos[1], model = pos[2];
     if (!afdb.empty() && !custom.empty())
         die(ERR_ARGPARSE, "Both afdb_lookup and custom_lookup are specified. Please specify only one.");
-    if (!afdb.empty()) die(ERR_MODULE_NOT_IMPLEMENTED, "createdb --afdb-lookup (DESIGN.md: next row f3)");
 
     std::string parent = parent_dir(output);
     if (parent.empty()) parent = ".";
@@ -103,6 +102,7 @@ static int createdb(int argc, char** argv) {
     std::vector<Record> found;
     std::vector<std::string> found_ss;
     if (!custom.empty()) split_by_lookup(custom, recs, found, found_ss);
+    if (!afdb.empty()) split_by_afdb(afdb, recs, found, found_ss);
     write_fasta(combined, recs);
     std::vector<std::string> ss;
     if (!recs.empty()) ss = predict_3di(model, recs, popt);
