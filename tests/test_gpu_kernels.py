@@ -125,3 +125,18 @@ def test_attention_peaked_scores(impl):
     ref = _attention_ref(qkv, cu, H, bias, md)
     assert np.isfinite(ctx.astype(np.float32)).all()
     assert np.abs(ctx.astype(np.float32) - ref).max() < 2e-2
+
+
+def test_gemm_fp16_outputs_saturate():
+    """Values beyond the fp16 range are stored as +-65504, not inf (same policy as the oracle's _r16)."""
+    lib = _lib.load()
+    M, N, K = 128, 256, 64
+    a = np.full((M, K), 200.0, np.float16)
+    b = np.full((N, K), 100.0, np.float16)
+    b[1::2] *= -1
+    for epi, want_neg in ((0, -65504.0), (1, 0.0)):
+        c = np.zeros((M, N), np.float16)
+        ms = C.c_float(0)
+        _lib.check(lib.p5_dbg_gemm(0, 1, epi, M, N, K, a.ctypes.data, b.ctypes.data, c.ctypes.data, 0, C.byref(ms)))
+        assert np.isfinite(c.astype(np.float32)).all()
+        assert (c[:, 0::2] == 65504.0).all() and (c[:, 1::2] == want_neg).all()

@@ -234,8 +234,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                 for (uint32_t q = 0; q < 4; ++q) {
                                     const float g0 = __uint_as_float(v[j * 16 + 4 * q]), u0 = __uint_as_float(v[j * 16 + 4 * q + 1]);
                                     const float g1 = __uint_as_float(v[j * 16 + 4 * q + 2]), u1 = __uint_as_float(v[j * 16 + 4 * q + 3]);
-                                    __half2 h = __floats2half2_rn(gelu_new(g0) * u0, gelu_new(g1) * u1);
-                                    pk[q] = *reinterpret_cast<uint32_t*>(&h);
+                                    pk[q] = ptx::pack_h2_sat(gelu_new(g0) * u0, gelu_new(g1) * u1);
                                 }
                                 *reinterpret_cast<uint4*>(crow + j * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             }
@@ -262,9 +261,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                 a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f);
                                 b0 = fmaxf(b0, 0.f); b1 = fmaxf(b1, 0.f);
                             }
-                            __half2 ha = __floats2half2_rn(a0, a1), hb = __floats2half2_rn(b0, b1);
-                            pk[i] = *reinterpret_cast<uint32_t*>(&ha);
-                            pk[16 + i] = *reinterpret_cast<uint32_t*>(&hb);
+                            pk[i] = ptx::pack_h2_sat(a0, a1);
+                            pk[16 + i] = ptx::pack_h2_sat(b0, b1);
                         }
                     } else {
                         ptx::tmem_ld_32x32b_x32(taddr + c * 32, pk);

@@ -17,12 +17,13 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {  // saturating fp16 pair (see ptx.cuh)
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ void store_half4(__half* p, float a, float b, float c, float d) {
-    __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&lo);
-    u.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(p) = u;
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_h2_sat(a, b), pack_h2_sat(c, d));
 }
 
 // d % 4 == 0.  Row kept in registers for d <= 1024 (kMaxIter float4 per lane), re-read otherwise.

@@ -30,6 +30,15 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
+// fp32 pair -> packed fp16x2 (lo in bits 0-15), round to nearest even, SATURATING: values beyond +-65504 become
+// +-65504 instead of inf.  T5-family activations are known to leave the fp16 range; an inf in a GEMM operand would
+// turn the whole residual row into NaN, a clamped value only loses that one element's magnitude (same policy in the
+// oracle's _r16).
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(
