@@ -58,3 +58,37 @@ def test_allgather_two_ranks_gloo(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert p.stdout.count("ok") == 2
+
+
+def test_python_db_writer_matches_format(tmp_path, tiny_dir):
+    """The rank-0 DB writer of createdb_dist produces a DB the reference's consumers accept, byte-identical to the
+    C++ writer's output for the same records."""
+    from oracle import host_oracle as H
+    from unicore_b200 import createdb_dist as CD
+    fasta = tmp_path / "combined_aa.fasta"
+    fasta.write_text(">unicore_aaaaaaaaaa\nMKTAYIAKQR\n>unicore_bbbbbbbbbb some desc\nGGGGG\nAA\n")
+    recs = CD.read_fasta_records(str(fasta))
+    assert recs == [(b"unicore_aaaaaaaaaa", b"MKTAYIAKQR"), (b"unicore_bbbbbbbbbb some desc", b"GGGGGAA")]
+    db = str(tmp_path / "db")
+    CD.write_foldseek_db(db, recs, [b"DVLVVVLCVV", b"PPPPPLL"], "combined_aa.fasta")
+    entries = H.check_foldseek_db(db)
+    assert entries == [("unicore_aaaaaaaaaa", "MKTAYIAKQR", "DVLVVVLCVV"), ("unicore_bbbbbbbbbb some desc", "GGGGGAA", "PPPPPLL")]
+    # same bytes as the C++ host writes (via the all-found custom-lookup path, which needs no GPU)
+    import subprocess
+    look = str(tmp_path / "look")
+    for suffix, rows in (("", [b"MKTAYIAKQR", b"GGGGGAA"]), ("_ss", [b"DVLVVVLCVV", b"PPPPPLL"])):
+        with open(look + suffix, "wb") as f:
+            for r in rows:
+                f.write(r + b"\n\0")
+    inp = tmp_path / "in"
+    inp.mkdir()
+    (inp / "Sp.fa").write_text(">a\nMKTAYIAKQR\n>b\nGGGGGAA\n")
+    out = tmp_path / "o" / "db"
+    p = subprocess.run([os.path.join(ROOT, "unicore_b200", "bin", "unicore-b200"), "createdb", str(inp), str(out),
+                        tiny_dir, "--custom-lookup", look, "-v", "0"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr  # every sequence is in the lookup DB: no device needed
+    cpp = H.check_foldseek_db(str(out))
+    recs2 = [(n.encode(), a.encode()) for n, a, _ in cpp]
+    CD.write_foldseek_db(str(tmp_path / "db2"), recs2, [s.encode() for _, _, s in cpp], "combined_aa.fasta")
+    for suffix in ("", ".index", ".dbtype", "_ss", "_ss.index", "_ss.dbtype", "_h", "_h.index", "_h.dbtype", ".lookup", ".source"):
+        assert open(str(out) + suffix, "rb").read() == open(str(tmp_path / "db2") + suffix, "rb").read(), suffix

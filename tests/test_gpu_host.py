@@ -107,3 +107,19 @@ def test_custom_lookup_partial(tmp_path, tiny_dir, tiny_oracle):
     entries = {aa: ss for _, aa, ss in H.check_foldseek_db(str(out))}
     assert entries[seqs[1]] == "V" * len(seqs[1]) and entries[seqs[3]] == "L" * len(seqs[3])
     _check_ss([(H.hashed_name(s), s, entries[s]) for s in (seqs[0], seqs[2])], tiny_oracle)
+
+
+def test_createdb_dist_single_rank(tmp_path, tiny_dir, tiny_oracle):
+    """The one-process-per-GPU entry (here world size 1; the N>1 path is the gloo test + bench.py --gpus N)."""
+    import sys
+    rng = np.random.default_rng(9)
+    recs = [(H.hashed_name(s), s) for s in (random_protein(rng, int(L)).decode() for L in (12, 90, 257))]
+    fasta = tmp_path / "combined_aa.fasta"
+    fasta.write_text("".join(f">{n}\n{s}\n" for n, s in recs))
+    db = tmp_path / "db"
+    p = subprocess.run([sys.executable, "-m", "unicore_b200.createdb_dist", str(fasta), str(db), "--prostt5-model", tiny_dir,
+                        "--threads", "4", "--gpu", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert p.returncode == 0, p.stderr
+    entries = H.check_foldseek_db(str(db))
+    assert [(n, a) for n, a, _ in entries] == recs
+    _check_ss(entries, tiny_oracle)
