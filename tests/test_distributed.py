@@ -24,6 +24,20 @@ def test_shards_partition_and_balance():
         assert D.shard_sizes(lens, world) == [int(lens[p].sum()) for p in parts]
 
 
+def test_scatter_shards_restores_input_order():
+    """Shard order (length-sorted, snake-dealt) -> input order, for every world size including 1 (the single-rank
+    createdb_dist run writes the DB in input order, not in the planner's order)."""
+    aa, off = spec.synthetic_proteome("config4", n=200)
+    lens = (off[1:] - off[:-1]).astype(np.int64)
+    want = ((aa.astype(np.int32) * 7 + 3) % 20 + 65).astype(np.uint8)
+    for world in (1, 2, 3, 8):
+        rows = []
+        for r in range(world):
+            laa, _ = D.take_shard(aa, off, D.shard_indices(lens, r, world))
+            rows.append(((laa.astype(np.int32) * 7 + 3) % 20 + 65).astype(np.uint8))
+        np.testing.assert_array_equal(D.scatter_shards(rows, lens, off), want)
+
+
 WORKER = r"""
 import os, sys
 import numpy as np

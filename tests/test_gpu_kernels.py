@@ -89,7 +89,7 @@ def _attention_ref(qkv, cu, H, bias, md):
     return out
 
 
-@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("impl", [1, 16, 0])
 @pytest.mark.parametrize("lens,H", [([1], 1), ([3], 1), ([64], 2), ([65, 1, 130], 2), ([352, 352], 4),
                                     ([700, 66, 1026], 2), ([2500], 1), ([128, 129, 127, 256, 257], 3)])
 def test_attention_matches_numpy(lens, H, impl):
@@ -109,6 +109,53 @@ def test_attention_matches_numpy(lens, H, impl):
     assert np.abs(ctx.astype(np.float32) - ref).max() < 4e-3
 
 
+def _many_lens(seed, n, lo, hi):
+    return [int(x) for x in np.random.default_rng(seed).integers(lo, hi, n)]
+
+
+# impl 16 + f: tcgen05 kernel with pipelining feature mask f (1 = TMA-fetched bias table, 2 = deferred epilogue and
+# item-spanning MMA stream, 4 = TMA-store epilogue).  Far more work items than resident CTAs (2 x 148), several
+# heads per CTA, ragged tails: every item-boundary path of the persistent kernel is taken many times.
+@pytest.mark.parametrize("impl", [1, 16, 17, 18, 20, 23, 0])
+@pytest.mark.parametrize("lens,H", [(_many_lens(1, 90, 3, 420), 5), (_many_lens(2, 400, 3, 70), 3),
+                                    ([352] * 40, 8), (_many_lens(3, 12, 900, 1500), 4)])
+def test_attention_many_items(lens, H, impl):
+    lib = _lib.load()
+    rng = np.random.default_rng(len(lens) + H)
+    cu = np.zeros(len(lens) + 1, np.int32)
+    cu[1:] = np.cumsum(lens)
+    M, md = int(cu[-1]), 128
+    qkv = (rng.standard_normal((M, 3 * H * 128), dtype=np.float32) * 0.6).astype(np.float16)
+    bias = (rng.standard_normal((H, 2 * md + 1), dtype=np.float32) * 0.5).astype(np.float32)
+    ctx = np.zeros((M, H * 128), np.float16)
+    ms = C.c_float(0)
+    _lib.check(lib.p5_dbg_attention(0, impl, qkv.ctypes.data, cu.ctypes.data, len(lens), H, md, bias.ctypes.data,
+                                    ctx.ctypes.data, 0, C.byref(ms)))
+    ref = _attention_ref(qkv, cu, H, bias, md)
+    assert np.abs(ctx.astype(np.float32) - ref).max() < 4e-3
+
+
+def test_attention_feature_variants_bit_identical():
+    """The pipelining features only reorder independent work: same bits out for every mask."""
+    lib = _lib.load()
+    lens, H, md = _many_lens(5, 120, 3, 500), 4, 128
+    rng = np.random.default_rng(11)
+    cu = np.zeros(len(lens) + 1, np.int32)
+    cu[1:] = np.cumsum(lens)
+    M = int(cu[-1])
+    qkv = (rng.standard_normal((M, 3 * H * 128), dtype=np.float32) * 0.8).astype(np.float16)
+    bias = (rng.standard_normal((H, 2 * md + 1), dtype=np.float32) * 0.5).astype(np.float32)
+    outs = []
+    for impl in (16, 17, 18, 19, 20, 21, 22, 23, 1):
+        ctx = np.zeros((M, H * 128), np.float16)
+        ms = C.c_float(0)
+        _lib.check(lib.p5_dbg_attention(0, impl, qkv.ctypes.data, cu.ctypes.data, len(lens), H, md, bias.ctypes.data,
+                                        ctx.ctypes.data, 0, C.byref(ms)))
+        outs.append(ctx)
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o.view(np.uint16), outs[0].view(np.uint16))
+
+
 @pytest.mark.parametrize("impl", [1, 0])
 def test_attention_peaked_scores(impl):
     """Un-scaled T5 scores can be large: one dominant key per row must not overflow or lose the row."""
@@ -121,6 +168,26 @@ def test_attention_peaked_scores(impl):
     ctx = np.zeros((T, 128), np.float16)
     ms = C.c_float(0)
     _lib.check(lib.p5_dbg_attention(0, impl, qkv.ctypes.data, cu.ctypes.data, 1, H, md, bias.ctypes.data,
+                                    ctx.ctypes.data, 0, C.byref(ms)))
+    ref = _attention_ref(qkv, cu, H, bias, md)
+    assert np.isfinite(ctx.astype(np.float32)).all()
+    assert np.abs(ctx.astype(np.float32) - ref).max() < 2e-2
+
+
+@pytest.mark.parametrize("impl", [1, 16, 0])
+def test_attention_peaked_scores_many_items(impl):
+    """Accumulator rescales (large un-scaled scores) while items are pipelined back to back in each CTA."""
+    lib = _lib.load()
+    rng = np.random.default_rng(9)
+    lens, H, md = _many_lens(9, 60, 150, 420), 6, 128
+    cu = np.zeros(len(lens) + 1, np.int32)
+    cu[1:] = np.cumsum(lens)
+    M = int(cu[-1])
+    qkv = (rng.standard_normal((M, 3 * H * 128), dtype=np.float32) * 3.0).astype(np.float16)
+    bias = (rng.standard_normal((H, 2 * md + 1), dtype=np.float32) * 0.5).astype(np.float32)
+    ctx = np.zeros((M, H * 128), np.float16)
+    ms = C.c_float(0)
+    _lib.check(lib.p5_dbg_attention(0, impl, qkv.ctypes.data, cu.ctypes.data, len(lens), H, md, bias.ctypes.data,
                                     ctx.ctypes.data, 0, C.byref(ms)))
     ref = _attention_ref(qkv, cu, H, bias, md)
     assert np.isfinite(ctx.astype(np.float32)).all()

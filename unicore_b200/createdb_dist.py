@@ -94,7 +94,7 @@ def main(argv=None):
         t1 = time.time()
         mine = pred.predict_packed(laa, loff, split_len=args.prostt5_split_length)
     t2 = time.time()
-    full = D.allgather_3di(mine, lens, off) if world > 1 else mine
+    full = D.allgather_3di(mine, lens, off) if world > 1 else D.scatter_shards([mine], lens, off)  # shard order -> input order
     t3 = time.time()
     if rank == 0:
         ss = [full[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(recs))]

@@ -141,7 +141,10 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         P5_CUDA(cudaSetDevice(device));
         attention_init_device();
         attention_tc_init_device();
-        P5_REQUIRE(impl == 0 || impl == 1, P5_ERR_ARG, "impl must be 0 (mma.sync) or 1 (tcgen05)");
+        // impl 16 + f = tcgen05 kernel with feature mask f (attention_tc.cu), for A/B tests of the pipelining features
+        P5_REQUIRE(impl == 0 || impl == 1 || (impl >= 16 && impl < 24), P5_ERR_ARG,
+                   "impl must be 0 (mma.sync), 1 (tcgen05) or 16..23 (tcgen05 with an explicit feature mask)");
+        const int features = impl >= 16 ? impl - 16 : -1;
         cudaDeviceProp prop;
         P5_CUDA(cudaGetDeviceProperties(&prop, device));
         const uint32_t M = uint32_t(cu_host[n_seq]);
@@ -165,6 +168,7 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         P5_CUDA(cudaMemcpy(qkv.p, qkv_host, M * 3 * inner * 2, cudaMemcpyHostToDevice));
         CUtensorMap tm_q = make_kmajor_tensor_map(qkv.p, Mpad, 3 * inner, 3 * inner, kAttnTcBlockM);
         CUtensorMap tm_kv = make_kmajor_tensor_map(qkv.p, Mpad, 3 * inner, 3 * inner, 64);
+        CUtensorMap tm_ctx = make_attn_store_tensor_map(ctx.p, M, inner);
         P5_CUDA(cudaMemcpy(cu.p, cu_host, (n_seq + 1) * 4, cudaMemcpyHostToDevice));
         P5_CUDA(cudaMemcpy(wk.p, work.data(), work.size() * sizeof(int2), cudaMemcpyHostToDevice));
         P5_CUDA(cudaMemcpy(wk4.p, work4.data(), work4.size() * sizeof(int4), cudaMemcpyHostToDevice));
@@ -173,10 +177,10 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         cudaStream_t st;
         P5_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         auto run = [&] {
-            if (impl == 1) {
-                launch_attention_tc(st, prop.multiProcessorCount, tm_q, tm_kv, static_cast<__half*>(ctx.p),
+            if (impl >= 1) {
+                launch_attention_tc(st, prop.multiProcessorCount, tm_q, tm_kv, tm_ctx, static_cast<__half*>(ctx.p),
                                     static_cast<const int4*>(wk4.p), uint32_t(work4.size()),
-                                    static_cast<const float*>(e_ext.p), n_head, max_dist);
+                                    static_cast<const float*>(e_ext.p), n_head, max_dist, features);
                 return;
             }
             launch_attention(st, static_cast<const __half*>(qkv.p), static_cast<__half*>(ctx.p),

@@ -10,9 +10,19 @@
 //   warp 4     TMA producer: Q (128 x 128), then K and V in 64-key tiles through two 2-stage rings
 //   warp 5     MMA issuer (one thread): S = Q.K^T (UMMA 128x64x16, both operands from 128B-swizzled
 //              smem) and O += P.V (UMMA 128x128x16, A = P from TMEM, B = V MN-major from smem)
-// The S for tile j+1 is issued before P.V of tile j, so the tensor pipe works on the next scores while
+// The S for tile g+1 is issued before P.V of tile g, so the tensor pipe works on the next scores while
 // the softmax warps are busy; the second resident CTA fills the remaining bubbles.
 // Work item = (sequence, 128-query tile, head); items are dealt round-robin to the persistent CTAs.
+//
+// Item boundaries are pipelined as well (template feature bits, all on by default):
+//   kFeatDefer  the MMA issuer walks the tiles of all its items as ONE stream (S of the next item's first tile is
+//               issued before P.V of this item's last tile) and the softmax warps run the O/l epilogue of item n
+//               AFTER the first tile of item n+1: they never idle on the P.V drain or on the next Q/K load.
+//   kFeatStore  the epilogue stages 32 rows x 64 B per warp in 64B-swizzled smem and leaves through TMA stores
+//               (whole sectors, asynchronous) instead of 16-byte per-thread stores 8 KB apart; warps whose 32 rows
+//               straddle the end of the sequence fall back to the direct stores.
+//   kFeatTable  the per-head bias table is fetched by the TMA producer (cp.async.bulk, two-slot full/empty ring),
+//               one head ahead, instead of by the softmax warps behind a named barrier.
 #include "kernels.h"
 
 #include <cstdlib>
@@ -34,8 +44,11 @@ constexpr uint32_t kSmemQ = 0;
 constexpr uint32_t kSmemK = kSmemQ + kQBytes;
 constexpr uint32_t kSmemV = kSmemK + 2 * kKVBytes;
 constexpr uint32_t kSmemE = kSmemV + 2 * kKVBytes;
-constexpr uint32_t kSmemBar = kSmemE + 2 * kEPad * 4;
-constexpr uint32_t kNumBars = 18;
+constexpr uint32_t kSmemStage = (kSmemE + 2 * kEPad * 4 + 511) / 512 * 512;  // epilogue staging: 2 KB per softmax warp
+constexpr uint32_t kStageBytes = 32 * 64;                                     // 32 rows x 32 fp16 columns
+constexpr uint32_t kSmemBar = kSmemStage + 4 * kStageBytes;
+constexpr uint32_t kNumBars = 22;
+constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4;
 constexpr uint32_t kSmemTotal = kSmemBar + kNumBars * 8 + 16;
 constexpr uint32_t kSmemDynamic = kSmemTotal + 1024;  // slack for manual 1024 B alignment
 constexpr uint32_t kTmemCols = 256;                   // O: [0,128)  S/P buffer 0: [128,192)  buffer 1: [192,256)
@@ -79,10 +92,13 @@ __device__ __forceinline__ Item get_item(uint32_t item, uint32_t n_work, const i
     return it;
 }
 
+template <uint32_t kF>
 __global__ void __launch_bounds__(kThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-                    __half* __restrict__ ctx, const int4* __restrict__ work, uint32_t n_work, uint32_t n_items,
-                    uint32_t H, const float* __restrict__ e_ext) {
+                    const __grid_constant__ CUtensorMap tm_ctx, __half* __restrict__ ctx,
+                    const int4* __restrict__ work, uint32_t n_work, uint32_t n_items, uint32_t H,
+                    const float* __restrict__ e_ext) {
+    constexpr bool kTable = (kF & kFeatTable) != 0, kDefer = (kF & kFeatDefer) != 0, kStore = (kF & kFeatStore) != 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
@@ -98,6 +114,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                                     // never two; with one barrier per tile parity the previous completion of
                                     // the same barrier (tile g-2) is always known to be complete (S_g was seen)
     uint64_t* o_empty = bars + 16;
+    uint64_t* e_full = bars + 18;   // [2] bias-table slots (kFeatTable)
+    uint64_t* e_empty = bars + 20;  // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + kNumBars);
     const uint32_t e_smem = ptx::smem_u32(smem + kSmemE);  // two bias tables of kEPad floats
 
@@ -114,6 +132,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             ptx::mbar_init(&v_empty[i], 1);
             ptx::mbar_init(&s_full[i], 1);
             ptx::mbar_init(&p_full[i], 4);  // one arrive per softmax warp
+            ptx::mbar_init(&e_full[i], 1);
+            ptx::mbar_init(&e_empty[i], 4);
         }
         ptx::mbar_init(&pv_done[0], 1);
         ptx::mbar_init(&pv_done[1], 1);
@@ -124,6 +144,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if (lane == 0) {
             ptx::prefetch_tensormap(&tm_q);
             ptx::prefetch_tensormap(&tm_kv);
+            if constexpr (kStore) ptx::prefetch_tensormap(&tm_ctx);
         }
         ptx::tmem_alloc<1>(tmem_ptr_smem, kTmemCols);
     }
@@ -138,9 +159,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     if (warp == 4) {
         // =============================== TMA producer ===============================
         if (lane == 0) {
-            uint32_t g = 0, n = 0;
+            uint32_t g = 0, n = 0, ek = 0;
+            int cur_h = -1;
             for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
                 const Item it = get_item(item, n_work, work);
+                if constexpr (kTable) {
+                    if (it.h != cur_h) {  // table load number ek goes to slot ek & 1, released by the 4 softmax warps
+                        cur_h = it.h;
+                        const uint32_t sl = ek & 1;
+                        if (ek >= 2) ptx::mbar_wait(&e_empty[sl], ((ek >> 1) & 1) ^ 1);
+                        ptx::mbar_arrive_expect_tx(&e_full[sl], kEPad * 4);
+                        ptx::bulk_load(smem + kSmemE + sl * kEPad * 4, e_ext + size_t(it.h) * kEPad, kEPad * 4, &e_full[sl]);
+                        ++ek;
+                    }
+                }
                 const int32_t qcol = it.h * int(kD);
                 const int32_t kcol = int(H * kD) + qcol;
                 const int32_t vcol = 2 * int(H * kD) + qcol;
@@ -170,12 +202,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             constexpr uint32_t idesc_s = ptx::make_idesc_f16_f32(kBM, kBN);
             constexpr uint32_t idesc_pv = ptx::make_idesc_f16_f32(kBM, kD) | ptx::kIdescBMnMajor;
             uint32_t g = 0, n = 0;
-            // O += P_gg . V_gg   (gg = global tile index, jj = index inside the item)
-            auto issue_pv = [&](uint32_t gg, uint32_t jj) {
+            // O += P_gg . V_gg   (gg = global tile index, jj = its index inside item number nn of this CTA)
+            auto issue_pv = [&](uint32_t gg, uint32_t jj, uint32_t nn) {
                 const uint32_t st = gg & 1, ph = (gg >> 1) & 1;
                 ptx::mbar_wait(&v_full[st], ph);
                 ptx::mbar_wait(&p_full[st], ph);
-                if (jj == 0 && n > 0) ptx::mbar_wait(o_empty, (n - 1) & 1);  // previous item's O has been read out
+                if (jj == 0 && nn > 0) ptx::mbar_wait(o_empty, (nn - 1) & 1);  // previous item's O has been read out
                 ptx::tc_fence_after();
                 const uint32_t a_tmem = tmem_base + 128 + st * kBN;
 #pragma unroll
@@ -187,6 +219,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 ptx::umma_commit<1>(&v_empty[st]);
                 ptx::umma_commit<1>(&pv_done[st]);
             };
+            bool have_prev = false;  // kDefer: tile g-1 (possibly of the previous item) still owes its P.V
+            uint32_t prev_jj = 0, prev_n = 0;
             for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
                 const Item it = get_item(item, n_work, work);
                 ptx::mbar_wait(q_full, n & 1);
@@ -206,31 +240,103 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     ptx::umma_commit<1>(&k_empty[st]);
                     ptx::umma_commit<1>(&s_full[st]);
                     if (j + 1 == it.nt) ptx::umma_commit<1>(q_empty);
-                    if (j >= 1) issue_pv(g - 1, j - 1);
+                    if constexpr (kDefer) {
+                        if (have_prev) issue_pv(g - 1, prev_jj, prev_n);
+                        have_prev = true;
+                        prev_jj = j;
+                        prev_n = n;
+                    } else {
+                        if (j >= 1) issue_pv(g - 1, j - 1, n);
+                    }
                 }
-                issue_pv(g - 1, it.nt - 1);
+                if constexpr (!kDefer) issue_pv(g - 1, it.nt - 1, n);
+            }
+            if constexpr (kDefer) {
+                if (have_prev) issue_pv(g - 1, prev_jj, prev_n);
             }
         }
     } else {
         // =============================== softmax warps ===============================
         const uint32_t r = warp * 32 + lane;  // row of the tile == TMEM lane
         const uint32_t t_lane = tmem_base + ((warp * 32u) << 16);
-        uint32_t g = 0, n = 0, e_buf = 0;
+        uint8_t* stage = smem + kSmemStage + warp * kStageBytes;
+        const uint32_t stage_row = ptx::smem_u32(stage) + lane * 64;
+        const uint32_t stage_xor = (lane >> 1) & 3u;  // SWIZZLE_64B: 16-byte chunk index ^= bits 7-8 of the address
+        uint32_t g = 0, n = 0, e_buf = 0, ek = 0;
         int cur_h = -1;
         uint32_t es = e_smem;
         float e_lo = 0.f, e_hi = 0.f;
+
+        // O / l -> ctx for the item whose tiles ended at global tile index g_end (exclusive).
+        //   row0 = first token row of this warp's 32 rows, valid = how many of them belong to the sequence
+        auto epilogue = [&](float inv, int row0, int valid, int h, uint32_t g_end, uint32_t nt) {
+            // the last two P.V (one per barrier) may both still be in flight: wait for both, older first
+            if (nt >= 2) ptx::mbar_wait(&pv_done[(g_end - 2) & 1], ((g_end - 2) >> 1) & 1);
+            ptx::mbar_wait(&pv_done[(g_end - 1) & 1], ((g_end - 1) >> 1) & 1);
+            ptx::tc_fence_after();
+            if (valid > 0) {
+                const bool use_tma = kStore && valid == 32;  // warp-uniform
+                __half* dst = ctx + size_t(row0 + int(lane)) * (size_t(H) * kD) + size_t(h) * kD;
+#pragma unroll 1
+                for (uint32_t c = 0; c < kD / 32; ++c) {
+                    uint32_t o[32], pk[16];
+                    ptx::tmem_ld_32x32b_x32(t_lane + c * 32, o);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        pk[i] = pack_h2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+                    if (use_tma) {
+                        if (lane == 0) ptx::bulk_wait_read<0>();  // the previous store has read the staging rows
+                        __syncwarp();
+#pragma unroll
+                        for (uint32_t q = 0; q < 4; ++q)
+                            ptx::sts_v4(stage_row + ((q ^ stage_xor) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                        ptx::fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_2d(&tm_ctx, stage, h * int(kD) + int(c * 32), row0);
+                            ptx::bulk_commit();
+                        }
+                    } else if (int(lane) < valid) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(o_empty);
+        };
+        bool pend = false;  // kDefer: the previous item still owes its epilogue
+        float p_inv = 0.f;
+        int p_row0 = 0, p_valid = 0, p_h = 0;
+        uint32_t p_g = 0, p_nt = 0;
+
         Item nxt = get_item(blockIdx.x, n_work, work);  // grid <= n_items
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
             const Item it = nxt;
             if (item + gridDim.x < n_items) nxt = get_item(item + gridDim.x, n_work, work);  // prefetch the next record
             if (it.h != cur_h) {
-                // other warps may still read the current table: write the other buffer, then meet
-                cur_h = it.h;
-                e_buf ^= 1;
-                es = e_smem + e_buf * kEPad * 4;
-                for (uint32_t i = threadIdx.x; i < 2 * kEHalf + 1; i += 128)
-                    sts_f32(es + i * 4, __ldg(e_ext + size_t(it.h) * kEPad + i));
-                ptx::named_bar_sync(1, 128);
+                if constexpr (kTable) {
+                    if (cur_h >= 0) {  // this warp is done with the previous head's table
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&e_empty[e_buf]);
+                    }
+                    cur_h = it.h;
+                    e_buf = ek & 1;
+                    es = e_smem + e_buf * kEPad * 4;
+                    ptx::mbar_wait(&e_full[e_buf], (ek >> 1) & 1);
+                    ++ek;
+                } else {
+                    // other warps may still read the current table: write the other buffer, then meet
+                    cur_h = it.h;
+                    e_buf ^= 1;
+                    es = e_smem + e_buf * kEPad * 4;
+                    for (uint32_t i = threadIdx.x; i < 2 * kEHalf + 1; i += 128)
+                        sts_f32(es + i * 4, __ldg(e_ext + size_t(it.h) * kEPad + i));
+                    ptx::named_bar_sync(1, 128);
+                }
                 e_lo = lds_f32(es);
                 e_hi = lds_f32(es + 2 * kEHalf * 4);
             }
@@ -320,44 +426,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&p_full[b]);
-            }
-            // ---- epilogue: O / l -> ctx ----
-            // the last two P.V (one per barrier) may both still be in flight: wait for both, older first
-            if (it.nt >= 2) ptx::mbar_wait(&pv_done[(g - 2) & 1], ((g - 2) >> 1) & 1);
-            ptx::mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
-            ptx::tc_fence_after();
-            const float inv = 1.f / l;
-            __half* dst = ctx + size_t(it.tok0 + row_seq) * (size_t(H) * kD) + size_t(it.h) * kD;
-#pragma unroll 1
-            for (uint32_t c = 0; c < kD / 64; ++c) {
-                uint32_t o0[32], o1[32];
-                ptx::tmem_ld_32x32b_x32(t_lane + c * 64, o0);
-                ptx::tmem_ld_32x32b_x32(t_lane + c * 64 + 32, o1);
-                ptx::tmem_ld_wait();
-                if (row_seq < it.T) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4 u;
-                        u.x = pack_h2(__uint_as_float(o0[8 * q + 0]) * inv, __uint_as_float(o0[8 * q + 1]) * inv);
-                        u.y = pack_h2(__uint_as_float(o0[8 * q + 2]) * inv, __uint_as_float(o0[8 * q + 3]) * inv);
-                        u.z = pack_h2(__uint_as_float(o0[8 * q + 4]) * inv, __uint_as_float(o0[8 * q + 5]) * inv);
-                        u.w = pack_h2(__uint_as_float(o0[8 * q + 6]) * inv, __uint_as_float(o0[8 * q + 7]) * inv);
-                        *reinterpret_cast<uint4*>(dst + c * 64 + q * 8) = u;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4 u;
-                        u.x = pack_h2(__uint_as_float(o1[8 * q + 0]) * inv, __uint_as_float(o1[8 * q + 1]) * inv);
-                        u.y = pack_h2(__uint_as_float(o1[8 * q + 2]) * inv, __uint_as_float(o1[8 * q + 3]) * inv);
-                        u.z = pack_h2(__uint_as_float(o1[8 * q + 4]) * inv, __uint_as_float(o1[8 * q + 5]) * inv);
-                        u.w = pack_h2(__uint_as_float(o1[8 * q + 6]) * inv, __uint_as_float(o1[8 * q + 7]) * inv);
-                        *reinterpret_cast<uint4*>(dst + c * 64 + 32 + q * 8) = u;
+                if constexpr (kDefer) {
+                    // the previous item's epilogue runs here, behind this item's first tile: its last P.V has had a
+                    // whole softmax tile of time to drain, and the tensor pipe already holds this item's next S
+                    if (j == 0 && pend) {
+                        epilogue(p_inv, p_row0, p_valid, p_h, p_g, p_nt);
+                        pend = false;
                     }
                 }
             }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(o_empty);
+            {
+                const int row0 = it.tok0 + it.q0 + int(warp * 32);
+                const int valid = min(32, max(0, it.T - (it.q0 + int(warp * 32))));
+                const float inv = 1.f / l;
+                if constexpr (kDefer) {
+                    pend = true;
+                    p_inv = inv; p_row0 = row0; p_valid = valid; p_h = it.h; p_g = g; p_nt = it.nt;
+                } else {
+                    epilogue(inv, row0, valid, it.h, g, it.nt);
+                }
+            }
+        }
+        if constexpr (kDefer) {
+            if (pend) epilogue(p_inv, p_row0, p_valid, p_h, p_g, p_nt);
+        }
+        if constexpr (kStore) {
+            if (lane == 0) ptx::bulk_wait<0>();  // all stores of this warp have completed before the CTA retires
         }
     }
     ptx::tc_fence_before();
@@ -367,9 +461,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
 }  // namespace
 
-void attention_tc_init_device() {
+namespace {
+using AttnKernel = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, __half*, const int4*, uint32_t, uint32_t, uint32_t,
+                            const float*);
+AttnKernel attn_kernel(uint32_t feat) {
+    switch (feat & 7u) {
+        case 0: return attention_tc_kernel<0>;
+        case 1: return attention_tc_kernel<1>;
+        case 2: return attention_tc_kernel<2>;
+        case 3: return attention_tc_kernel<3>;
+        case 4: return attention_tc_kernel<4>;
+        case 5: return attention_tc_kernel<5>;
+        case 6: return attention_tc_kernel<6>;
+        default: return attention_tc_kernel<7>;
+    }
+}
+}  // namespace
 
-    P5_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemDynamic)));
+void attention_tc_init_device() {
+    for (uint32_t f = 0; f < 8; ++f)
+        P5_CUDA(cudaFuncSetAttribute(attn_kernel(f), cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemDynamic)));
 }
 
 // extended, log2-domain bias table of one model: e_ext[h][kAttnTcTable] with
@@ -383,16 +494,24 @@ void attention_tc_build_table(const float* bias, uint32_t H, uint32_t max_dist, 
         }
 }
 
-void launch_attention_tc(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, const CUtensorMap& tm_kv, __half* ctx,
-                         const int4* work128, uint32_t n_work, const float* e_ext, uint32_t H, uint32_t max_dist) {
+int attention_tc_default_features() {
+    static const int f = getenv("P5_ATTN_FEAT") ? (atoi(getenv("P5_ATTN_FEAT")) & 7) : 7;  // experiment knob
+    return f;
+}
+
+void launch_attention_tc(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, const CUtensorMap& tm_kv,
+                         const CUtensorMap& tm_ctx, __half* ctx, const int4* work128, uint32_t n_work,
+                         const float* e_ext, uint32_t H, uint32_t max_dist, int features) {
     if (n_work == 0) return;
     P5_REQUIRE(max_dist <= 128, P5_ERR_UNSUPPORTED,
                "relative attention max distance %u: the tcgen05 attention kernel assumes <= 128", max_dist);
+    P5_REQUIRE((reinterpret_cast<uintptr_t>(e_ext) & 15) == 0, P5_ERR_ARG, "attention bias table is not 16-byte aligned");
     const uint64_t n_items = uint64_t(n_work) * H;
     P5_REQUIRE(n_items < (1ull << 31), P5_ERR_UNSUPPORTED, "too many attention work items");
     static const int ctas_per_sm = getenv("P5_ATTN_CTAS") ? atoi(getenv("P5_ATTN_CTAS")) : 2;  // experiment knob
     const uint32_t grid = uint32_t(std::min<uint64_t>(n_items, uint64_t(ctas_per_sm * num_sms)));
-    attention_tc_kernel<<<grid, kThreads, kSmemDynamic, st>>>(tm_q, tm_kv, ctx, work128, n_work, uint32_t(n_items), H, e_ext);
+    const uint32_t feat = uint32_t(features < 0 ? attention_tc_default_features() : features);
+    attn_kernel(feat)<<<grid, kThreads, kSmemDynamic, st>>>(tm_q, tm_kv, tm_ctx, ctx, work128, n_work, uint32_t(n_items), H, e_ext);
     P5_CUDA(cudaGetLastError());
 }
 

@@ -9,6 +9,7 @@
 
 #include "common.h"
 #include "gemm.cuh"
+#include "kernels.h"
 
 namespace p5 {
 
@@ -65,6 +66,22 @@ static CUtensorMap make_c_tensor_map(void* ptr, bool f16, uint64_t rows, uint64_
                                    gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     P5_REQUIRE(r == CUDA_SUCCESS, P5_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed with CUresult %d", (int)r);
+    return m;
+}
+
+// Store descriptor of the attention output ctx [rows, cols] fp16 (kernels.h): box = 32 rows x 32 columns (64 B),
+// 64-byte swizzle; one box is what a softmax warp stages per epilogue step.
+CUtensorMap make_attn_store_tensor_map(void* ctx, uint64_t rows, uint64_t cols) {
+    P5_REQUIRE((reinterpret_cast<uintptr_t>(ctx) & 15) == 0 && cols % 8 == 0, P5_ERR_ARG, "attention output is not 16-byte aligned");
+    CUtensorMap m;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * 2};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ctx, gdim, gstride, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    P5_REQUIRE(r == CUDA_SUCCESS, P5_ERR_CUDA, "cuTensorMapEncodeTiled (attention output) failed with CUresult %d", (int)r);
     return m;
 }
 

@@ -30,13 +30,16 @@ void attention_init_device();  // once per device, with that device current
 // Same computation on the tcgen05 tensor cores (attention_tc.cu): persistent kernel, work128[n_work] =
 // (first token of the sequence, its token count, first query row of the 128-row tile, 0), e_ext = extended log2-domain bias table built by
 // attention_tc_build_table ([H][kAttnTcTable] floats), tm_q / tm_kv = TMA descriptors of the qkv buffer
-// with 128-row and 64-row boxes of 64 columns.
+// with 128-row and 64-row boxes of 64 columns, tm_ctx = store descriptor of ctx (make_attn_store_tensor_map).
+// features: bit mask of the kernel's pipelining features (attention_tc.cu), -1 = default (all, or P5_ATTN_FEAT).
 constexpr uint32_t kAttnTcBlockM = 128;
 constexpr uint32_t kAttnTcTable = 644;
 void attention_tc_init_device();
 void attention_tc_build_table(const float* bias, uint32_t H, uint32_t max_dist, float* e_ext);
-void launch_attention_tc(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, const CUtensorMap& tm_kv, __half* ctx,
-                         const int4* work128, uint32_t n_work, const float* e_ext, uint32_t H, uint32_t max_dist);
+CUtensorMap make_attn_store_tensor_map(void* ctx, uint64_t rows, uint64_t cols);  // box 32 rows x 32 columns, 64B swizzle
+void launch_attention_tc(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, const CUtensorMap& tm_kv,
+                         const CUtensorMap& tm_ctx, __half* ctx, const int4* work128, uint32_t n_work,
+                         const float* e_ext, uint32_t H, uint32_t max_dist, int features = -1);
 
 constexpr uint32_t kAttnBlockM = 64;  // query rows per attention work item
 constexpr uint32_t kHeadChunk = 64;   // residues per head work item

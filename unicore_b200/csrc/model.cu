@@ -209,7 +209,7 @@ public:
     // workspace for `cap` tokens
     uint32_t cap = 0;
     DevBuf h, xn, qkv, ctx, ffn, taps;
-    CUtensorMap tm_xn, tm_ctx, tm_ffn, tm_q, tm_kv;
+    CUtensorMap tm_xn, tm_ctx, tm_ffn, tm_q, tm_kv, tm_ctx_st;
 
     Slot slots[2];
     std::deque<DevBuf> staged_meta;   // one per staged batch on this device
@@ -525,6 +525,7 @@ void DeviceCtx::ensure_workspace(uint32_t tokens) {
     tm_ffn = make_kmajor_tensor_map(ffn.p, n, ff, ff, kGemmBlockM);
     tm_q = make_kmajor_tensor_map(qkv.p, n, 3 * inner, 3 * inner, kAttnTcBlockM);
     tm_kv = make_kmajor_tensor_map(qkv.p, n, 3 * inner, 3 * inner, 64);
+    tm_ctx_st = make_attn_store_tensor_map(ctx.p, n, inner);
     cap = n;
 }
 
@@ -580,7 +581,7 @@ void DeviceCtx::forward(const MetaLayout& l, const int32_t* meta_d, uint8_t* let
         gemm(Epi::StoreF16, tm_xn, L.tm_qkv, qkv.p, 3 * inner, d);
         prof_begin(PC_ATTN);
         if (opt.attn_impl == 1 && e_ext)
-            launch_attention_tc(stream, num_sms, tm_q, tm_kv, ctx.as<__half>(), aw128, l.n_aw128, e_ext, hp.n_head,
+            launch_attention_tc(stream, num_sms, tm_q, tm_kv, tm_ctx_st, ctx.as<__half>(), aw128, l.n_aw128, e_ext, hp.n_head,
                                 hp.max_distance);
         else
             launch_attention(stream, qkv.as<__half>(), ctx.as<__half>(), cu, aw, l.n_aw, bias, hp.n_head, hp.max_distance);

@@ -161,6 +161,15 @@ __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint64_t*
         : "memory");
 }
 
+// Plain (non-tensor) bulk copy global -> smem; `bytes` a multiple of 16, both addresses 16-byte aligned;
+// completion is credited to `bar` like a tensor load.
+__device__ __forceinline__ void bulk_load(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem)),
+                 "l"(reinterpret_cast<uint64_t>(gmem)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // 2-D tiled store smem -> global (bulk async group of the issuing thread); out-of-bounds parts of the
 // box are clipped by the tensor map.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int32_t c0, int32_t c1) {

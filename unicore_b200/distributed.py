@@ -37,6 +37,21 @@ def take_shard(aa: np.ndarray, offsets: np.ndarray, idx: np.ndarray):
     return out, off
 
 
+def scatter_shards(rows, lengths: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+    """rows[r] = the letters rank r emitted (packed in its shard order, padding ignored) -> the letters of ALL
+    sequences at `offsets` (input order)."""
+    world = len(rows)
+    out = np.zeros(int(offsets[-1]), np.uint8)
+    for r in range(world):
+        pos = 0
+        row = rows[r]
+        for i in shard_indices(lengths, r, world):
+            n = int(lengths[i])
+            out[int(offsets[i]):int(offsets[i]) + n] = row[pos:pos + n]
+            pos += n
+    return out
+
+
 def allgather_3di(local: np.ndarray, lengths: np.ndarray, offsets: np.ndarray, device=None) -> np.ndarray:
     """Every rank passes the letters of its shard (packed in shard order); returns the letters of ALL
     sequences at `offsets` (input order).  Uses the default torch.distributed process group."""
@@ -55,13 +70,4 @@ def allgather_3di(local: np.ndarray, lengths: np.ndarray, offsets: np.ndarray, d
     recv = torch.empty(world * slab, dtype=torch.uint8, device=dev)
     dist.all_gather_into_tensor(recv, send)
     recv = recv.cpu().numpy().reshape(world, slab)
-    out = np.zeros(int(offsets[-1]), np.uint8)
-    for r in range(world):
-        idx = shard_indices(lengths, r, world)
-        pos = 0
-        row = recv[r]
-        for i in idx:
-            n = int(lengths[i])
-            out[int(offsets[i]):int(offsets[i]) + n] = row[pos:pos + n]
-            pos += n
-    return out
+    return scatter_shards(recv, lengths, offsets)
