@@ -4,8 +4,7 @@
 
 Shapes: config 2 (256 x 352 tokens x 32 heads), a config-4-like ragged mix and a config-5-like long mix.
 impl 16 + f runs feature mask f (1 = TMA-fetched bias table, 2 = deferred epilogue + item-spanning MMA stream,
-4 = TMA-store epilogue, 8 = streamed softmax tiles, 16 = next-tile load overlapped with the P store,
-32 = K requested one tile ahead of V); impl 0 is the mma.sync kernel.  Every variant is also compared bit for bit with mask 0.
+4 = TMA-store epilogue, 8 = one tcgen05.commit per event); impl 0 is the mma.sync kernel.  Every variant is also compared bit for bit with mask 0.
 """
 import argparse
 import ctypes as C
@@ -51,7 +50,7 @@ def main():
         flops = 4.0 * 128 * H * float(sum(t * t for t in lens))
         base = None
         row = {}
-        for impl in (16, 23, 48, 55, 63, 79, 0):
+        for impl in (16, 17, 18, 20, 23, 31, 0):
             ctx, ms = run(lib, impl, qkv, cu, H, bias, a.iters)
             if base is None:
                 base = ctx

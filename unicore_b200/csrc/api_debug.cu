@@ -142,8 +142,8 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         attention_init_device();
         attention_tc_init_device();
         // impl 16 + f = tcgen05 kernel with feature mask f (attention_tc.cu), for A/B tests of the pipelining features
-        P5_REQUIRE(impl == 0 || impl == 1 || (impl >= 16 && impl < 80), P5_ERR_ARG,
-                   "impl must be 0 (mma.sync), 1 (tcgen05) or 16..79 (tcgen05 with an explicit feature mask)");
+        P5_REQUIRE(impl == 0 || impl == 1 || (impl >= 16 && impl < 32), P5_ERR_ARG,
+                   "impl must be 0 (mma.sync), 1 (tcgen05) or 16..31 (tcgen05 with an explicit feature mask)");
         const int features = impl >= 16 ? impl - 16 : -1;
         cudaDeviceProp prop;
         P5_CUDA(cudaGetDeviceProperties(&prop, device));

@@ -21,24 +21,17 @@
 //   kFeatStore  the epilogue stages 32 rows x 64 B per warp in 64B-swizzled smem and leaves through TMA stores
 //               (whole sectors, asynchronous) instead of 16-byte per-thread stores 8 KB apart; warps whose 32 rows
 //               straddle the end of the sequence fall back to the direct stores.
-//   kFeatStream every key tile but an item's first is processed as a stream of four 16-column chunks against the
-//               running reference maximum (the next chunk's tcgen05.ld is in flight while this one goes through
-//               FFMA / EX2 / pack), instead of load-all, max, then exp: the MUFU starts after one chunk and the
-//               TMEM latency is paid once per tile.  A tile whose maximum outgrows the reference (the rare
-//               rescale case) is redone on the two-pass path; S is still intact because P is stored last.
-//   kFeatOverlap (with kFeatStream) the first chunk of the NEXT tile of the item is requested from TMEM between the
-//               store of P and its tcgen05.wait::st, when that tile's S has already landed (a non-blocking probe):
-//               the store latency, the load latency and the barrier arrive overlap instead of adding up.
-//   kFeatKAhead the TMA producer requests K one tile ahead of V (K_{g+1} before V_g, across item boundaries): a K
-//               slot is free as soon as S of two tiles back has been computed, a V slot only after the P.V of two
-//               tiles back, so with the strict K_g, V_g order the next K (and with it the next S) left one softmax
-//               tile late and the softmax warps stalled on S whenever a tile took less than the TMA latency.
 //   kFeatTable  the per-head bias table is fetched by the TMA producer (cp.async.bulk, two-slot full/empty ring),
 //               one head ahead, instead of by the softmax warps behind a named barrier.
+//   kFeatBars   one tcgen05.commit per event instead of two: s_full doubles as "K slot free" and pv_done as
+//               "V slot free" (the producer waits on the same barriers as the softmax warps), 3 instead of 5
+//               commits per tile on the single MMA-issuing thread.
+// Tried and dropped (profiles/r01/README.md): streaming the softmax in 16-column chunks against the running
+// maximum, overlapping the next tile's tcgen05.ld with the P store, requesting K one tile ahead of V, and L2
+// prefetches (cp.async.bulk.prefetch.tensor) of the coming Q/K/V tiles.
 #include "kernels.h"
 
 #include <cstdlib>
-#include <type_traits>
 
 #include "common.h"
 #include "gemm_launch.h"
@@ -61,8 +54,7 @@ constexpr uint32_t kSmemStage = (kSmemE + 2 * kEPad * 4 + 511) / 512 * 512;  // 
 constexpr uint32_t kStageBytes = 32 * 64;                                     // 32 rows x 32 fp16 columns
 constexpr uint32_t kSmemBar = kSmemStage + 4 * kStageBytes;
 constexpr uint32_t kNumBars = 22;
-constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatStream = 8, kFeatOverlap = 16,
-                   kFeatKAhead = 32;
+constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatBars = 8;
 constexpr uint32_t kSmemTotal = kSmemBar + kNumBars * 8 + 16;
 constexpr uint32_t kSmemDynamic = kSmemTotal + 1024;  // slack for manual 1024 B alignment
 constexpr uint32_t kTmemCols = 256;                   // O: [0,128)  S/P buffer 0: [128,192)  buffer 1: [192,256)
@@ -113,17 +105,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     const int4* __restrict__ work, uint32_t n_work, uint32_t n_items, uint32_t H,
                     const float* __restrict__ e_ext) {
     constexpr bool kTable = (kF & kFeatTable) != 0, kDefer = (kF & kFeatDefer) != 0, kStore = (kF & kFeatStore) != 0,
-                   kStream = (kF & kFeatStream) != 0, kOverlap = kStream && (kF & kFeatOverlap) != 0,
-                   kKAhead = (kF & kFeatKAhead) != 0;
+                   kBars = (kF & kFeatBars) != 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
     uint64_t* q_full = bars + 0;
     uint64_t* q_empty = bars + 1;
     uint64_t* k_full = bars + 2;   // [2]
-    uint64_t* k_empty = bars + 4;  // [2]
+    uint64_t* k_empty = kBars ? bars + 10 : bars + 4;  // [2]  (kFeatBars: == s_full)
     uint64_t* v_full = bars + 6;   // [2]
-    uint64_t* v_empty = bars + 8;  // [2]
+    uint64_t* v_empty = kBars ? bars + 14 : bars + 8;  // [2]  (kFeatBars: == pv_done)
     uint64_t* s_full = bars + 10;  // [2]
     uint64_t* p_full = bars + 12;  // [2]
     uint64_t* pv_done = bars + 14;  // [2]: P.V of even / odd tiles.  A waiter may lag ONE phase behind an mbarrier,
@@ -207,44 +198,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 ptx::tma_load_2d(&tm_kv, full, dst, col, row, ptx::kEvictNormal);
                 ptx::tma_load_2d(&tm_kv, full, dst + kKVBytes / 2, col + 64, row, ptx::kEvictNormal);
             };
-            if constexpr (kKAhead) {
-                // two cursors over the CTA's flat tile stream: K runs one tile ahead of V
-                struct Cur {
-                    uint32_t item, n, j, g;
-                    Item it;
-                };
-                auto advance = [&](Cur& c) {
-                    ++c.g;
-                    if (++c.j == c.it.nt) {
-                        c.item += gridDim.x;
-                        ++c.n;
-                        c.j = 0;
-                        if (c.item < n_items) c.it = get_item(c.item, n_work, work);
-                    }
-                };
-                Cur kc{blockIdx.x, 0, 0, 0, get_item(blockIdx.x, n_work, work)};  // grid <= n_items
-                Cur vc = kc;
-                load_q(kc.it, 0);
-                load_kv(kc.it, 0, 0, 0);
-                advance(kc);
-                while (vc.item < n_items) {
-                    if (kc.item < n_items) {
-                        if (kc.j == 0) load_q(kc.it, kc.n);
-                        load_kv(kc.it, kc.j, kc.g, 0);
-                        advance(kc);
-                    }
-                    load_kv(vc.it, vc.j, vc.g, 1);
-                    advance(vc);
-                }
-            } else {
-                uint32_t g = 0, n = 0;
-                for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
-                    const Item it = get_item(item, n_work, work);
-                    load_q(it, n);
-                    for (uint32_t j = 0; j < it.nt; ++j, ++g) {
-                        load_kv(it, j, g, 0);
-                        load_kv(it, j, g, 1);
-                    }
+            uint32_t g = 0, n = 0;
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+                const Item it = get_item(item, n_work, work);
+                load_q(it, n);
+                for (uint32_t j = 0; j < it.nt; ++j, ++g) {
+                    load_kv(it, j, g, 0);
+                    load_kv(it, j, g, 1);
                 }
             }
         }
@@ -268,7 +228,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     const uint64_t b = ptx::make_mnmajor_sw128_desc(sV + st * kKVBytes + ks * 2048, kKVBytes / 2, 1024);
                     ptx::umma_f16_ts(tmem_base, a_tmem + ks * 8, b, idesc_pv, (jj | ks) != 0u);
                 }
-                ptx::umma_commit<1>(&v_empty[st]);
+                if constexpr (!kBars) ptx::umma_commit<1>(&v_empty[st]);
                 ptx::umma_commit<1>(&pv_done[st]);
             };
             bool have_prev = false;  // kDefer: tile g-1 (possibly of the previous item) still owes its P.V
@@ -289,7 +249,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                         const uint64_t b = ptx::make_kmajor_sw128_desc(sK + st * kKVBytes + half * (kKVBytes / 2)) + kk * 2;
                         ptx::umma_f16<1>(d_tmem, a, b, idesc_s, ks != 0u);
                     }
-                    ptx::umma_commit<1>(&k_empty[st]);
+                    if constexpr (!kBars) ptx::umma_commit<1>(&k_empty[st]);
                     ptx::umma_commit<1>(&s_full[st]);
                     if (j + 1 == it.nt) ptx::umma_commit<1>(q_empty);
                     if constexpr (kDefer) {
@@ -360,53 +320,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(o_empty);
         };
-        // One key tile as a stream of 16-column chunks against the reference maximum m_ref (same arithmetic, same
-        // summation order as the two-pass path).  Returns true when the tile's maximum outgrew the reference:
-        // nothing has been committed then and the caller redoes the tile on the two-pass path.
-        auto stream_tile = [&](auto const_tag, auto tail_tag, uint32_t s_addr, float e_c, uint32_t er, int n_valid,
-                               float m_ref, float& l_io, uint32_t (&pk)[32], uint32_t (&ca)[16], bool preloaded) -> bool {
-            constexpr bool kConst = decltype(const_tag)::value, kTail = decltype(tail_tag)::value;
-            uint32_t cb[16];
-            if (!preloaded) ptx::tmem_ld_32x32b_x16(s_addr, ca);
-            ptx::tmem_ld_wait();
-            float sa = 0.f, sb = 0.f, sc = 0.f, sd = 0.f;
-            float mxa = -INFINITY, mxb = -INFINITY, mxc = -INFINITY, mxd = -INFINITY;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t(&cur)[16] = (q & 1) ? cb : ca;
-                uint32_t(&nxt)[16] = (q & 1) ? ca : cb;
-                if (q < 3) ptx::tmem_ld_32x32b_x16(s_addr + 16 * (q + 1), nxt);
-                if (!kTail || q * 16 < n_valid) {
-                    float z[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float bias = kConst ? e_c : lds_f32(er + uint32_t(q * 16 + i) * 4);
-                        z[i] = fmaf(__uint_as_float(cur[i]), kLog2e, bias);
-                        if (kTail && q * 16 + i >= n_valid) z[i] = -INFINITY;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        mxa = fmaxf(mxa, z[i]);
-                        mxb = fmaxf(mxb, z[i + 1]);
-                        mxc = fmaxf(mxc, z[i + 2]);
-                        mxd = fmaxf(mxd, z[i + 3]);
-                        const float p0 = ex2(z[i] - m_ref), p1 = ex2(z[i + 1] - m_ref);
-                        const float p2 = ex2(z[i + 2] - m_ref), p3 = ex2(z[i + 3] - m_ref);
-                        sa += p0; sb += p1; sc += p2; sd += p3;
-                        pk[q * 8 + i / 2] = pack_h2(p0, p1);
-                        pk[q * 8 + i / 2 + 1] = pack_h2(p2, p3);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) pk[q * 8 + i] = 0u;
-                }
-                if (q < 3) ptx::tmem_ld_wait();
-            }
-            const float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
-            if (__any_sync(0xffffffffu, mx > m_ref + kRescaleThreshold)) return true;
-            l_io += (sa + sb) + (sc + sd);
-            return false;
-        };
         bool pend = false;  // kDefer: the previous item still owes its epilogue
         float p_inv = 0.f;
         int p_row0 = 0, p_valid = 0, p_h = 0;
@@ -442,15 +355,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             const int row_seq = it.q0 + int(r);
             float m = -INFINITY, l = 0.f;
             const bool warp_valid = it.q0 + int(warp * 32) < it.T;
-            uint32_t pre[16];        // kOverlap: first 16 columns of the next tile's S, requested early
-            bool preloaded = false;  // warp-uniform
             for (uint32_t j = 0; j < it.nt; ++j, ++g) {
                 const uint32_t b = g & 1, ph = (g >> 1) & 1;
                 const int j0 = int(j * kBN);
-                if (!preloaded) {  // (a preloaded tile has been seen complete already)
-                    ptx::mbar_wait(&s_full[b], ph);
-                    ptx::tc_fence_after();
-                }
+                ptx::mbar_wait(&s_full[b], ph);
+                ptx::tc_fence_after();
                 uint32_t pk[32];
                 if (!warp_valid) {  // all 32 query rows lie past the end of the sequence: keep the protocol going only
 #pragma unroll
@@ -461,22 +370,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 const bool bias_const = dmax <= -128 || dmin >= 128;
                 const float e_c = dmax <= -128 ? e_lo : e_hi;
                 const uint32_t er = es + uint32_t(int(kEHalf) - row_seq + j0) * 4;
-                bool two_pass = true;
-                if constexpr (kStream) {
-                    if (j > 0) {
-                        const uint32_t s_addr = t_lane + 128 + b * kBN;
-                        const int n_valid = it.T - j0;
-                        using T_ = std::true_type;
-                        using F_ = std::false_type;
-                        if (n_valid >= int(kBN))
-                            two_pass = bias_const ? stream_tile(T_{}, F_{}, s_addr, e_c, er, n_valid, m, l, pk, pre, preloaded)
-                                                  : stream_tile(F_{}, F_{}, s_addr, e_c, er, n_valid, m, l, pk, pre, preloaded);
-                        else
-                            two_pass = bias_const ? stream_tile(T_{}, T_{}, s_addr, e_c, er, n_valid, m, l, pk, pre, preloaded)
-                                                  : stream_tile(F_{}, T_{}, s_addr, e_c, er, n_valid, m, l, pk, pre, preloaded);
-                    }
-                }
-                if (two_pass) {
                 uint32_t v0[32], v1[32];
                 ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN, v0);
                 ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN + 32, v1);
@@ -542,16 +435,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 }
                 l += (sa + sb) + (sc + sd);
                 }
-                }
                 ptx::tmem_st_32x32b_x32(t_lane + 128 + b * kBN, pk);  // P over the first 32 columns of S
-                preloaded = false;
-                if constexpr (kOverlap) {
-                    if (warp_valid && j + 1 < it.nt && ptx::mbar_test(&s_full[b ^ 1], ((g + 1) >> 1) & 1)) {
-                        ptx::tc_fence_after();
-                        ptx::tmem_ld_32x32b_x16(t_lane + 128 + (b ^ 1) * kBN, pre);
-                        preloaded = true;
-                    }
-                }
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -601,18 +485,15 @@ AttnKernel attn_kernel(uint32_t feat) {
         case 2: return attention_tc_kernel<2>;
         case 4: return attention_tc_kernel<4>;
         case 7: return attention_tc_kernel<7>;
+        case 8: return attention_tc_kernel<8>;
         case 15: return attention_tc_kernel<15>;
-        case 32: return attention_tc_kernel<32>;
-        case 39: return attention_tc_kernel<39>;
-        case 47: return attention_tc_kernel<47>;
-        case 63: return attention_tc_kernel<63>;
         default: throw Error(P5_ERR_ARG, strf("attention feature mask %u is not built", feat));
     }
 }
 }  // namespace
 
 void attention_tc_init_device() {
-    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 15u, 32u, 39u, 47u, 63u})
+    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 15u})
         P5_CUDA(cudaFuncSetAttribute(attn_kernel(f), cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemDynamic)));
 }
 
@@ -628,7 +509,7 @@ void attention_tc_build_table(const float* bias, uint32_t H, uint32_t max_dist, 
 }
 
 int attention_tc_default_features() {
-    static const int f = getenv("P5_ATTN_FEAT") ? atoi(getenv("P5_ATTN_FEAT")) : 39;  // experiment knob
+    static const int f = getenv("P5_ATTN_FEAT") ? atoi(getenv("P5_ATTN_FEAT")) : 15;  // experiment knob
     return f;
 }
 
