@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""DRAM traffic of the two K-heavy projections under ncu, per launch, for a few launch knobs (experiments only):
+P5_GEMM_BAND (tile order), P5_GEMM_CLUSTERS (CTA pairs used), P5_GEMM_PROMO (TMA L2 promotion).
+
+    python tools/sweep_gemm_traffic.py > gpurun_out/gemm_traffic.txt
+"""
+import csv, ctypes as C, io, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+SHAPES = {"o": (2, 90112, 1024, 4096), "ffn_out": (2, 90112, 1024, 16384), "ffn_in": (1, 90112, 16384, 1024)}
+if len(sys.argv) > 1 and sys.argv[1] == "--one":
+    from unicore_b200 import _lib
+    lib = _lib.load()
+    epi, M, N, K = SHAPES[sys.argv[2]]
+    ms = C.c_float(0)
+    rc = lib.p5_dbg_gemm_bench(0, 1, epi, M, N, K, 2, C.byref(ms))
+    sys.exit(rc)
+CONFIGS = [{}, {"P5_GEMM_CLUSTERS": "72"}, {"P5_GEMM_PROMO": "2"}, {"P5_GEMM_PROMO": "0"}, {"P5_GEMM_BAND": "2"},
+           {"P5_GEMM_CLUSTERS": "72", "P5_GEMM_PROMO": "2"}, {"P5_GEMM_CLUSTERS": "64"}]
+names = sys.argv[1:] or ["ffn_out", "o"]
+for name in names:
+    for cfg in CONFIGS:
+        env = dict(os.environ)
+        for k in ("P5_GEMM_CLUSTERS", "P5_GEMM_PROMO", "P5_GEMM_BAND"):
+            env.pop(k, None)
+        env.update(cfg)
+        p = subprocess.run(["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum",
+                            "--clock-control", "none", "-k", "regex:gemm_tcgen05", "-s", "3", "-c", "2", "--csv",
+                            sys.executable, __file__, "--one", name], capture_output=True, text=True, timeout=600, env=env)
+        rows = [r for r in csv.reader(io.StringIO(p.stdout)) if len(r) > 5 and r[0].isdigit()]
+        out = {}
+        for r in rows:
+            out.setdefault(r[-3], []).append(r[-1] + " " + r[-2])
+        print(name, json.dumps(cfg), json.dumps(out), flush=True)
+        if not rows:
+            print(p.stdout[-500:], p.stderr[-500:])

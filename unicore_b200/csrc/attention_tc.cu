@@ -486,6 +486,7 @@ AttnKernel attn_kernel(uint32_t feat) {
         case 4: return attention_tc_kernel<4>;
         case 7: return attention_tc_kernel<7>;
         case 8: return attention_tc_kernel<8>;
+        case 14: return attention_tc_kernel<14>;
         case 15: return attention_tc_kernel<15>;
         default: throw Error(P5_ERR_ARG, strf("attention feature mask %u is not built", feat));
     }
@@ -493,7 +494,7 @@ AttnKernel attn_kernel(uint32_t feat) {
 }  // namespace
 
 void attention_tc_init_device() {
-    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 15u})
+    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u})
         P5_CUDA(cudaFuncSetAttribute(attn_kernel(f), cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemDynamic)));
 }
 

@@ -46,9 +46,15 @@ CUtensorMap make_kmajor_tensor_map(const void* ptr, uint64_t rows, uint64_t cols
     cuuint64_t gstride[1] = {ld * 2};
     cuuint32_t box[2] = {kGemmBlockK, box_rows};
     cuuint32_t estr[2] = {1, 1};
+    // P5_GEMM_PROMO (traffic experiments only): L2 promotion of operand loads, 0 none / 1 64 B / 2 128 B / 3 256 B
+    static const int promo = getenv("P5_GEMM_PROMO") ? atoi(getenv("P5_GEMM_PROMO")) : 3;
+    const CUtensorMapL2promotion l2p = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                       : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                       : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                    : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box,
-                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     P5_REQUIRE(r == CUDA_SUCCESS, P5_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return m;
 }
@@ -98,6 +104,8 @@ void launch_one(cudaStream_t stream, int num_sms, const CUtensorMap& ta, const C
     const uint32_t num_nt = (s.N + kBlockN - 1) / kBlockN;
     const uint32_t tiles = num_mt * num_nt;
     uint32_t clusters = static_cast<uint32_t>(num_sms / kCtaGroup);
+    static const uint32_t max_clusters = getenv("P5_GEMM_CLUSTERS") ? uint32_t(atoi(getenv("P5_GEMM_CLUSTERS"))) : 0u;  // experiment knob
+    if (max_clusters && max_clusters < clusters) clusters = max_clusters;
     if (tiles < clusters) clusters = tiles;
     if (clusters == 0) return;
     cudaLaunchConfig_t cfg = {};
