@@ -33,7 +33,8 @@ int p5_dbg_gemm_bench(int device, int variant, int epilogue, uint32_t M, uint32_
                       float* ms_out);
 
 /* Relative-position-bias attention over packed sequences, in isolation.
- * impl: 1 = tcgen05 kernel (attention_tc.cu, the product default), 0 = mma.sync kernel (attention.cu).
+ * impl: 1 = tcgen05 kernel (attention_tc.cu, the product default), 0 = mma.sync kernel (attention.cu),
+ * 16 + f = tcgen05 kernel with pipelining-feature mask f (the built masks are listed in attention_tc.cu; A/B tests).
  * qkv_host [M, 3*n_head*128] fp16 (Q | K | V), cu_host [n_seq+1] token offsets (M = cu_host[n_seq]),
  * bias_host [n_head, 2*max_dist+1] fp32 (natural-log domain, indexed by clamp(key-query)+max_dist),
  * ctx_host [M, n_head*128] fp16 out.  iters>0: mean ms per launch over `iters` launches in *ms_out. */
