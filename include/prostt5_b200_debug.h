@@ -41,6 +41,12 @@ int p5_dbg_gemm_bench(int device, int variant, int epilogue, uint32_t M, uint32_
 int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, const int32_t* cu_host, uint32_t n_seq, uint32_t n_head,
                      uint32_t max_dist, const float* bias_host, uint16_t* ctx_host, int iters, float* ms_out);
 
+/* Timing probe of the SM partition (csrc/partition.cu): one encoder layer's four projections + attention of
+ * n_seq sequences of T tokens, sequentially on all SMs (out[0], ms per iteration) against two half-batches on a
+ * device split into gemm_sms SMs and the rest: GEMM side alone (out[1]), attention side alone (out[2]), both
+ * together (out[3] GEMM side, out[4] attention side); out[5], out[6] = SM counts provisioned.  out has 8 floats. */
+int p5_dbg_partition_probe(int device, int gemm_sms, uint32_t n_seq, uint32_t T, int iters, float* out);
+
 /* Thread-local message of the last failed call on this thread (also declared in prostt5_b200.h). */
 const char* p5_last_error(void);
 
