@@ -195,6 +195,31 @@ def test_attention_peaked_scores_many_items(impl):
     assert np.abs(ctx.astype(np.float32) - ref).max() < 2e-2
 
 
+@pytest.mark.parametrize("impl", [1, 16, 0])
+def test_attention_is_independent_of_the_neighbour_sequence(impl):
+    """Packed layout: the query rows past a sequence's end are the next sequence's tokens.  They must not leak into the
+    sequence's own rows - not even through the warp-wide vote that triggers an accumulator rescale (peaked scores make
+    those frequent).  Found on a 1-GPU vs 2-GPU createdb whose _ss files differed in a few residues."""
+    lib = _lib.load()
+    rng = np.random.default_rng(17)
+    H, md = 2, 128
+    bias = (rng.standard_normal((H, 2 * md + 1), dtype=np.float32) * 0.5).astype(np.float32)
+    first = (rng.standard_normal((200, 3 * H * 128), dtype=np.float32) * 3.0).astype(np.float16)  # 200 = 128 + 64 + 8
+    outs = []
+    for seed, scale, n2 in ((1, 3.0, 300), (2, 6.0, 77), (3, 0.1, 500)):
+        r2 = np.random.default_rng(seed)
+        second = (r2.standard_normal((n2, 3 * H * 128), dtype=np.float32) * scale).astype(np.float16)
+        qkv = np.concatenate([first, second])
+        cu = np.array([0, 200, 200 + n2], np.int32)
+        ctx = np.zeros((200 + n2, H * 128), np.float16)
+        ms = C.c_float(0)
+        _lib.check(lib.p5_dbg_attention(0, impl, qkv.ctypes.data, cu.ctypes.data, 2, H, md, bias.ctypes.data,
+                                        ctx.ctypes.data, 0, C.byref(ms)))
+        outs.append(ctx[:200].copy())
+    np.testing.assert_array_equal(outs[0].view(np.uint16), outs[1].view(np.uint16))
+    np.testing.assert_array_equal(outs[0].view(np.uint16), outs[2].view(np.uint16))
+
+
 def test_gemm_fp16_outputs_saturate():
     """Values beyond the fp16 range are stored as +-65504, not inf (same policy as the oracle's _r16)."""
     lib = _lib.load()

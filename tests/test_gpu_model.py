@@ -220,6 +220,26 @@ def test_config2_properties(full):
         assert full.encode_debug(s)[2] == a[int(off[i]):int(off[i + 1])].tobytes()
 
 
+def test_full_size_ragged_batching_invariance(full):
+    """Config-4-like ragged lengths at full size (scores large enough for accumulator rescales): the letters of a
+    sequence do not depend on the batch it lands in nor on its neighbours there (one-GPU and N-GPU createdb runs must
+    write the same _ss bytes)."""
+    aa, off = spec.synthetic_proteome("config4", n=300)
+    lens = (off[1:] - off[:-1]).astype(np.int64)
+    a = full.predict_packed(aa, off)
+    # other batch boundaries, other neighbours: reversed input order and a small token budget
+    order = np.arange(len(lens))[::-1]
+    seqs = [aa[int(off[i]):int(off[i + 1])].tobytes() for i in order]
+    full.set_option("max_batch_tokens", 30000)
+    got = full.predict(seqs)
+    full.set_option("max_batch_tokens", 94720)
+    for k, i in enumerate(order):
+        assert got[k] == a[int(off[i]):int(off[i + 1])].tobytes(), f"sequence {i} (length {lens[i]})"
+    for i in (0, 17, 123):
+        s = aa[int(off[i]):int(off[i + 1])].tobytes()
+        assert full.encode_debug(s)[2] == a[int(off[i]):int(off[i + 1])].tobytes()
+
+
 def test_in_process_multi_device(tiny_dir):
     """Two devices in one process (threads + shared batch queue) give the bytes of one device."""
     import torch

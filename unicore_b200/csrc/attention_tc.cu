@@ -405,7 +405,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 const float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
                 if (j == 0) {
                     m = mx + kHeadRoom;  // key 0 is always valid, so mx is finite
-                } else if (__any_sync(0xffffffffu, mx > m + kRescaleThreshold)) {
+                } else if (__any_sync(0xffffffffu, row_seq < it.T && mx > m + kRescaleThreshold)) {
+                    // (rows past the end of the sequence are the NEXT sequence's tokens: they must not take part in
+                    // the vote, or a sequence's 3Di would depend on its neighbour in the batch)
                     // rescale the O accumulator of this warp's 32 rows (rare after the first tiles)
                     const float m_new = fmaxf(m, mx + kHeadRoom);
                     const float alpha = ex2(m - m_new);
