@@ -240,6 +240,17 @@ def test_full_size_ragged_batching_invariance(full):
         assert full.encode_debug(s)[2] == a[int(off[i]):int(off[i + 1])].tobytes()
 
 
+def test_attention_implementations_agree_at_full_size(full):
+    """The tcgen05 kernel and the independent mma.sync kernel differ only in rounding (fp16 P against different
+    running maxima): the letters they give must agree on nearly every residue of a ragged full-size batch."""
+    aa, off = spec.synthetic_proteome("config4", n=60)
+    a = full.predict_packed(aa, off)
+    full.set_option("attn_impl", 0)
+    b = full.predict_packed(aa, off)
+    full.set_option("attn_impl", 1)
+    assert (a != b).mean() < 0.01
+
+
 def test_in_process_multi_device(tiny_dir):
     """Two devices in one process (threads + shared batch queue) give the bytes of one device."""
     import torch
