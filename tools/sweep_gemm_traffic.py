@@ -13,15 +13,20 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
     lib = _lib.load()
     epi, M, N, K = SHAPES[sys.argv[2]]
     ms = C.c_float(0)
-    rc = lib.p5_dbg_gemm_bench(0, 1, epi, M, N, K, 2, C.byref(ms))
+    iters = int(os.environ.get("SWEEP_ITERS", "2"))
+    rc = lib.p5_dbg_gemm_bench(0, 1, epi, M, N, K, iters, C.byref(ms))
+    if iters > 2:
+        print("TIMING", sys.argv[2], iters, "iters:", round(ms.value, 4), "ms =", round(2.0 * M * N * K / ms.value * 1e-9, 1), "TFLOP/s")
     sys.exit(rc)
 CONFIGS = [{}, {"P5_GEMM_CLUSTERS": "72"}, {"P5_GEMM_PROMO": "2"}, {"P5_GEMM_PROMO": "0"}, {"P5_GEMM_BAND": "2"},
            {"P5_GEMM_CLUSTERS": "72", "P5_GEMM_PROMO": "2"}, {"P5_GEMM_CLUSTERS": "64"}]
+if os.environ.get("SWEEP_CLUSTER_ONLY"):  # cluster-size experiment: pairs sharing a row tile in one 4- / 8-CTA cluster
+    CONFIGS = [{}, {"P5_GEMM_CLUSTER": "8"}, {"P5_GEMM_CLUSTER": "4"}]
 names = sys.argv[1:] or ["ffn_out", "o"]
 for name in names:
     for cfg in CONFIGS:
         env = dict(os.environ)
-        for k in ("P5_GEMM_CLUSTERS", "P5_GEMM_PROMO", "P5_GEMM_BAND"):
+        for k in ("P5_GEMM_CLUSTERS", "P5_GEMM_PROMO", "P5_GEMM_BAND", "P5_GEMM_CLUSTER", "SWEEP_ITERS"):
             env.pop(k, None)
         env.update(cfg)
         p = subprocess.run(["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum",
@@ -34,3 +39,7 @@ for name in names:
         print(name, json.dumps(cfg), json.dumps(out), flush=True)
         if not rows:
             print(p.stdout[-500:], p.stderr[-500:])
+        if os.environ.get("SWEEP_CLUSTER_ONLY"):  # sustained timing of the same configuration, outside ncu
+            env["SWEEP_ITERS"] = "300"
+            t = subprocess.run([sys.executable, __file__, "--one", name], capture_output=True, text=True, timeout=600, env=env)
+            print("   ", [l for l in (t.stdout + t.stderr).splitlines() if l.startswith("TIMING") or "co-resident" in l], flush=True)

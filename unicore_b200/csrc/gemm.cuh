@@ -90,7 +90,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
     const uint32_t warp_idx = threadIdx.x >> 5;  // warp-uniform
     const uint32_t lane = ptx::lane_id();
-    const uint32_t cta_rank = (kCtaGroup == 2) ? ptx::cluster_ctarank() : 0u;
+    // The CTA pair of cta_group::2 is (2i, 2i+1) of the cluster; the launch may put several pairs in one cluster
+    // (experiment: the pairs sharing a row tile of A co-scheduled on one GPC), so ranks are taken pair-relative.
+    const uint32_t cluster_rank = (kCtaGroup == 2) ? ptx::cluster_ctarank() : 0u;
+    const uint32_t cta_rank = cluster_rank & 1u;
+    const uint32_t leader_rank = cluster_rank & ~1u;
     const bool is_leader = cta_rank == 0;
 
     if (warp_idx == 0 && lane == 0) {
@@ -147,7 +151,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         if (is_leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes * 2);
                         ptx::tma_load_2d_pair(&tma_a, &full_bar[stage], sa, k_idx, m_idx, ptx::kEvictNormal);
                         ptx::tma_load_2d_pair(&tma_b, &full_bar[stage], sb, k_idx, n_idx, ptx::kEvictLast);
-                        if (!is_leader) ptx::mbar_arrive_cluster(&full_bar[stage], 0);
+                        if (!is_leader) ptx::mbar_arrive_cluster(&full_bar[stage], leader_rank);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -176,8 +180,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                             const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
                             ptx::umma_f16<kCtaGroup>(tmem_d, a_desc + koff, b_desc + koff, idesc, (kb | k) != 0u);
                         }
-                        ptx::umma_commit<kCtaGroup>(&empty_bar[stage]);  // smem slot free when MMAs retire
-                        if (kb == num_kb - 1) ptx::umma_commit<kCtaGroup>(&tmem_full_bar[as]);
+                        ptx::umma_commit<kCtaGroup>(&empty_bar[stage], leader_rank);  // smem slot free when MMAs retire
+                        if (kb == num_kb - 1) ptx::umma_commit<kCtaGroup>(&tmem_full_bar[as], leader_rank);
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -212,7 +216,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 __syncwarp();
                 if (lane == 0) {
                     if constexpr (kCtaGroup == 1) ptx::mbar_arrive(&tmem_empty_bar[as]);
-                    else ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+                    else ptx::mbar_arrive_cluster(&tmem_empty_bar[as], leader_rank);
                 }
             };
             if constexpr (kEpi == Epi::GatedGeluF16) {

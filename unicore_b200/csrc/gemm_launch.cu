@@ -4,6 +4,8 @@
 
 #include <cuda.h>
 
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 
@@ -108,6 +110,32 @@ void launch_one(cudaStream_t stream, int num_sms, const CUtensorMap& ta, const C
     if (max_clusters && max_clusters < clusters) clusters = max_clusters;
     if (tiles < clusters) clusters = tiles;
     if (clusters == 0) return;
+    // P5_GEMM_CLUSTER=8 (traffic experiment, pair variant): four pairs = the N tiles of one row tile per cluster
+    static const uint32_t cluster_ctas = getenv("P5_GEMM_CLUSTER") ? uint32_t(atoi(getenv("P5_GEMM_CLUSTER"))) : 0u;
+    uint32_t cluster_dim = kCtaGroup;
+    if (kCtaGroup == 2 && cluster_ctas > 2 && cluster_ctas % 2 == 0 && cluster_ctas <= 8) {
+        const uint32_t pairs_per = cluster_ctas / 2;
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3(cluster_ctas * 64, 1, 1);
+        q.blockDim = dim3(kGemmThreads, 1, 1);
+        q.dynamicSmemBytes = L::kDynamic;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = cluster_ctas;
+        qa[0].val.clusterDim.y = 1;
+        qa[0].val.clusterDim.z = 1;
+        q.attrs = qa;
+        q.numAttrs = 1;
+        int fit = 0;
+        P5_CUDA(cudaOccupancyMaxActiveClusters(&fit, kernel, &q));
+        static bool said = false;
+        if (!said) { fprintf(stderr, "p5: GEMM clusters of %u CTAs: %d co-resident\n", cluster_ctas, fit); said = true; }
+        const uint32_t rounded = std::min(clusters / pairs_per * pairs_per, uint32_t(fit > 0 ? fit : 0) * pairs_per);
+        if (rounded >= pairs_per) {  // (a problem smaller than one big cluster keeps the plain pair launch)
+            clusters = rounded;
+            cluster_dim = cluster_ctas;
+        }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * kCtaGroup, 1, 1);
     cfg.blockDim = dim3(kGemmThreads, 1, 1);
@@ -115,7 +143,7 @@ void launch_one(cudaStream_t stream, int num_sms, const CUtensorMap& ta, const C
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCtaGroup;
+    attr[0].val.clusterDim.x = cluster_dim;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;

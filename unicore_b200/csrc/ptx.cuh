@@ -256,13 +256,13 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 // Make `bar` (same offset in every CTA of `mask` for the pair variant) observe completion of all
 // previously issued MMAs of this thread.  Implies tcgen05.fence::before_thread_sync.
 template <int kCtaGroup>
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint32_t leader_rank = 0) {  // leader_rank: even rank of the pair
     if constexpr (kCtaGroup == 1) {
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                          smem_u32(bar))
                      : "memory");
     } else {
-        const uint16_t mask = 0x3;
+        const uint16_t mask = uint16_t(0x3u << leader_rank);
         asm volatile(
             "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
                 "r"(smem_u32(bar)),
