@@ -64,7 +64,7 @@ int p5_token_table(const p5_model* m, int32_t* lut256);
 int p5_bias_table(const p5_model* m, uint32_t head, float* out);
 
 /* Options (all have defaults):
- *   "max_batch_tokens"  tokens packed into one forward pass (default 94720 = 370 GEMM row tiles)
+ *   "max_batch_tokens"  tokens packed into one forward pass (default 92160 = 360 GEMM row tiles)
  *   "head_include_eos"  1 (default): the </s> row is part of the CNN head's input, as in the Rostlab
  *                       ProstT5 script applied to a batch of one; 0: zero padding starts right after the
  *                       last residue

@@ -98,7 +98,7 @@ def test_batching_invariance_and_order(tiny):
     seqs[7] = b""  # empty records are allowed and produce nothing
     seqs[20] = seqs[3]
     single = [tiny.encode_debug(s)[2] if s else b"" for s in seqs]
-    tiny.set_option("max_batch_tokens", 94720)
+    tiny.set_option("max_batch_tokens", 92160)
     assert tiny.predict(seqs) == single
     tiny.set_option("max_batch_tokens", 512)  # many small batches, two in flight
     assert tiny.predict(seqs) == single
@@ -106,7 +106,7 @@ def test_batching_invariance_and_order(tiny):
     assert st["batches"] > 10 and st["residues"] == sum(map(len, seqs))
     tiny.set_option("max_batch_tokens", 64)  # every sequence longer than the budget gets its own batch
     assert tiny.predict(seqs) == single
-    tiny.set_option("max_batch_tokens", 94720)
+    tiny.set_option("max_batch_tokens", 92160)
     assert all(set(s) <= set(b"ACDEFGHIKLMNPQRSTVWY") for s in single)
     assert single[20] == single[3]
 
@@ -124,7 +124,7 @@ def test_staged_equals_streaming(tiny):
     out2 = np.zeros(len(aa), np.uint8)
     tiny.run_staged(out2)  # repeatable
     np.testing.assert_array_equal(out2, want)
-    tiny.set_option("max_batch_tokens", 94720)
+    tiny.set_option("max_batch_tokens", 92160)
 
 
 def test_gemm_variants_agree(tiny):
@@ -212,7 +212,7 @@ def test_config2_properties(full):
     np.testing.assert_array_equal(a, b)
     full.set_option("max_batch_tokens", 20000)
     c = full.predict_packed(aa, off)
-    full.set_option("max_batch_tokens", 94720)
+    full.set_option("max_batch_tokens", 92160)
     np.testing.assert_array_equal(a, c)
     assert full.stats()["residues"] == 89600
     for i in (0, 100, 255):
@@ -232,7 +232,7 @@ def test_full_size_ragged_batching_invariance(full):
     seqs = [aa[int(off[i]):int(off[i + 1])].tobytes() for i in order]
     full.set_option("max_batch_tokens", 30000)
     got = full.predict(seqs)
-    full.set_option("max_batch_tokens", 94720)
+    full.set_option("max_batch_tokens", 92160)
     for k, i in enumerate(order):
         assert got[k] == a[int(off[i]):int(off[i + 1])].tobytes(), f"sequence {i} (length {lens[i]})"
     for i in (0, 17, 123):

@@ -22,11 +22,14 @@ CONFIGS = [{}, {"P5_GEMM_CLUSTERS": "72"}, {"P5_GEMM_PROMO": "2"}, {"P5_GEMM_PRO
            {"P5_GEMM_CLUSTERS": "72", "P5_GEMM_PROMO": "2"}, {"P5_GEMM_CLUSTERS": "64"}]
 if os.environ.get("SWEEP_CLUSTER_ONLY"):  # cluster-size experiment: pairs sharing a row tile in one 4- / 8-CTA cluster
     CONFIGS = [{}, {"P5_GEMM_CLUSTER": "8"}, {"P5_GEMM_CLUSTER": "4"}]
+if os.environ.get("SWEEP_PREFER_ONLY"):
+    os.environ["SWEEP_CLUSTER_ONLY"] = "1"
+    CONFIGS = [{}, {"P5_GEMM_CLUSTER": "8", "P5_GEMM_PREFER": "1"}, {"P5_GEMM_CLUSTERS": "72"}]
 names = sys.argv[1:] or ["ffn_out", "o"]
 for name in names:
     for cfg in CONFIGS:
         env = dict(os.environ)
-        for k in ("P5_GEMM_CLUSTERS", "P5_GEMM_PROMO", "P5_GEMM_BAND", "P5_GEMM_CLUSTER", "SWEEP_ITERS"):
+        for k in ("P5_GEMM_CLUSTERS", "P5_GEMM_PROMO", "P5_GEMM_BAND", "P5_GEMM_CLUSTER", "P5_GEMM_PREFER", "SWEEP_ITERS"):
             env.pop(k, None)
         env.update(cfg)
         p = subprocess.run(["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum",

@@ -110,30 +110,43 @@ void launch_one(cudaStream_t stream, int num_sms, const CUtensorMap& ta, const C
     if (max_clusters && max_clusters < clusters) clusters = max_clusters;
     if (tiles < clusters) clusters = tiles;
     if (clusters == 0) return;
-    // P5_GEMM_CLUSTER=8 (traffic experiment, pair variant): four pairs = the N tiles of one row tile per cluster
-    static const uint32_t cluster_ctas = getenv("P5_GEMM_CLUSTER") ? uint32_t(atoi(getenv("P5_GEMM_CLUSTER"))) : 0u;
-    uint32_t cluster_dim = kCtaGroup;
+    // K-heavy projections (O, FFN-out): the CTA pairs working on the N tiles of one row tile stream the same A rows.
+    // When those pairs sit on both dies each L2 partition fetches its own copy from HBM (FFN-out read 4.8-7.3 GB
+    // per launch instead of 3.4 GB, depending on the box's SM-to-die map).  Asking for 8-CTA clusters as the
+    // PREFERRED cluster dimension makes the device co-schedule four consecutive pairs (= the four N tiles of a row
+    // tile when N = 1024) on one GPC wherever it can (15 such clusters fit) and fall back to plain pairs for the
+    // rest, so every pair of the grid stays resident: -40 % DRAM reads and +8 % sustained on FFN-out, +3 % on O
+    // (profiles/r01/gemm_prefer_sweep.txt).  The grid is rounded down to a multiple of four pairs (72 of 74).
+    // P5_GEMM_CLUSTER = 2 turns it off, 8 forces it for every shape; P5_GEMM_PREFER=0 makes 8 the regular dimension
+    // (experiments).
+    static const int cluster_env = getenv("P5_GEMM_CLUSTER") ? atoi(getenv("P5_GEMM_CLUSTER")) : 0;
+    static const bool prefer = !(getenv("P5_GEMM_PREFER") && atoi(getenv("P5_GEMM_PREFER")) == 0);
+    uint32_t cluster_dim = kCtaGroup, preferred_dim = 0;
+    const bool k_heavy = s.K >= 2048 && num_nt % 4 == 0 && num_nt <= 8;
+    const uint32_t cluster_ctas = cluster_env ? uint32_t(cluster_env) : (k_heavy ? 8u : 2u);
     if (kCtaGroup == 2 && cluster_ctas > 2 && cluster_ctas % 2 == 0 && cluster_ctas <= 8) {
         const uint32_t pairs_per = cluster_ctas / 2;
-        cudaLaunchConfig_t q = {};
-        q.gridDim = dim3(cluster_ctas * 64, 1, 1);
-        q.blockDim = dim3(kGemmThreads, 1, 1);
-        q.dynamicSmemBytes = L::kDynamic;
-        cudaLaunchAttribute qa[1];
-        qa[0].id = cudaLaunchAttributeClusterDimension;
-        qa[0].val.clusterDim.x = cluster_ctas;
-        qa[0].val.clusterDim.y = 1;
-        qa[0].val.clusterDim.z = 1;
-        q.attrs = qa;
-        q.numAttrs = 1;
-        int fit = 0;
-        P5_CUDA(cudaOccupancyMaxActiveClusters(&fit, kernel, &q));
-        static bool said = false;
-        if (!said) { fprintf(stderr, "p5: GEMM clusters of %u CTAs: %d co-resident\n", cluster_ctas, fit); said = true; }
-        const uint32_t rounded = std::min(clusters / pairs_per * pairs_per, uint32_t(fit > 0 ? fit : 0) * pairs_per);
+        uint32_t rounded = clusters / pairs_per * pairs_per;
+        if (!prefer) {  // every cluster must be a big one: only as many as fit at once
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(cluster_ctas * 64, 1, 1);
+            q.blockDim = dim3(kGemmThreads, 1, 1);
+            q.dynamicSmemBytes = L::kDynamic;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = cluster_ctas;
+            qa[0].val.clusterDim.y = 1;
+            qa[0].val.clusterDim.z = 1;
+            q.attrs = qa;
+            q.numAttrs = 1;
+            int fit = 0;
+            P5_CUDA(cudaOccupancyMaxActiveClusters(&fit, kernel, &q));
+            rounded = std::min(rounded, uint32_t(fit > 0 ? fit : 0) * pairs_per);
+        }
         if (rounded >= pairs_per) {  // (a problem smaller than one big cluster keeps the plain pair launch)
             clusters = rounded;
-            cluster_dim = cluster_ctas;
+            if (prefer) preferred_dim = cluster_ctas;
+            else cluster_dim = cluster_ctas;
         }
     }
     cudaLaunchConfig_t cfg = {};
@@ -141,13 +154,20 @@ void launch_one(cudaStream_t stream, int num_sms, const CUtensorMap& ta, const C
     cfg.blockDim = dim3(kGemmThreads, 1, 1);
     cfg.dynamicSmemBytes = L::kDynamic;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cluster_dim;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (preferred_dim) {
+        attr[1].id = cudaLaunchAttributePreferredClusterDimension;
+        attr[1].val.preferredClusterDim.x = preferred_dim;
+        attr[1].val.preferredClusterDim.y = 1;
+        attr[1].val.preferredClusterDim.z = 1;
+        cfg.numAttrs = 2;
+    }
     P5_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, tc, C, s));
 }
 

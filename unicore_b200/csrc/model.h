@@ -76,7 +76,7 @@ struct Stats {
 };
 
 struct Options {
-    uint32_t max_batch_tokens = 94720;
+    uint32_t max_batch_tokens = 92160;
     int head_include_eos = 1;
     int gemm_variant = 1;
     int profile = 0;
