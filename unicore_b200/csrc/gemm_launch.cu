@@ -161,12 +161,19 @@ void launch_one(cudaStream_t stream, int num_sms, const CUtensorMap& ta, const C
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (preferred_dim) {
+    static bool preferred_ok = true;  // cleared if this driver rejects the attribute (it needs CUDA 12.8+)
+    if (preferred_dim && preferred_ok) {
         attr[1].id = cudaLaunchAttributePreferredClusterDimension;
         attr[1].val.preferredClusterDim.x = preferred_dim;
         attr[1].val.preferredClusterDim.y = 1;
         attr[1].val.preferredClusterDim.z = 1;
         cfg.numAttrs = 2;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ta, tb, tc, C, s);
+        if (e == cudaSuccess) return;
+        if (e != cudaErrorInvalidValue && e != cudaErrorNotSupported) P5_CUDA(e);
+        (void)cudaGetLastError();  // the plain pair launch below computes the same thing
+        preferred_ok = false;
+        cfg.numAttrs = 1;
     }
     P5_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, tc, C, s));
 }
