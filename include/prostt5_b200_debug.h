@@ -41,6 +41,21 @@ int p5_dbg_gemm_bench(int device, int variant, int epilogue, uint32_t M, uint32_
 int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, const int32_t* cu_host, uint32_t n_seq, uint32_t n_head,
                      uint32_t max_dist, const float* bias_host, uint16_t* ctx_host, int iters, float* ms_out);
 
+/* RMSNorm in isolation (csrc/kernels.cu).  ids_host == NULL: xn = fp16(rmsnorm(h) * w) for
+ * h_host [M, d] fp32, optionally also the fp32 value in f32_host.  ids_host != NULL: the layer-0 form, h = E[ids]
+ * (embd_host [n_vocab, d] fp16) written to h_out_host [M, d] fp32 and normalised into xn_host [M, d] fp16. */
+int p5_dbg_rmsnorm(int device, const int32_t* ids_host, const uint16_t* embd_host, uint32_t n_vocab, const float* h_host,
+                   const float* w_host, float eps, uint32_t M, uint32_t d, float* h_out_host, uint16_t* xn_host,
+                   float* f32_host);
+
+/* CNN-head tail in isolation (§8a p10, p11): taps_host [M, ksize*c1] fp32 (tap-major conv0 partial products of every
+ * token row), cu_host [n_seq+1] token offsets; b0 [c1], w1 [n_cls, c1, ksize], b1 [n_cls].  Residue r of sequence s
+ * is token row cu[s] + 1 + r.  letters_host [sum L] (one of "ACDEFGHIKLMNPQRSTVWY" per residue), logits_host optional
+ * [sum L, n_cls] fp32. */
+int p5_dbg_head(int device, const float* taps_host, const int32_t* cu_host, uint32_t n_seq, const float* b0_host,
+                const float* w1_host, const float* b1_host, uint32_t c1, uint32_t n_cls, uint32_t ksize, int include_eos,
+                uint8_t* letters_host, float* logits_host);
+
 /* Timing probe of the SM partition (csrc/partition.cu): one encoder layer's four projections + attention of
  * n_seq sequences of T tokens, sequentially on all SMs (out[0], ms per iteration) against two half-batches on a
  * device split into gemm_sms SMs and the rest: GEMM side alone (out[1]), attention side alone (out[2]), both

@@ -233,3 +233,122 @@ def test_gemm_fp16_outputs_saturate():
         _lib.check(lib.p5_dbg_gemm(0, 1, epi, M, N, K, a.ctypes.data, b.ctypes.data, c.ctypes.data, 0, C.byref(ms)))
         assert np.isfinite(c.astype(np.float32)).all()
         assert (c[:, 0::2] == 65504.0).all() and (c[:, 1::2] == want_neg).all()
+
+
+def _rmsnorm_ref(x, w, eps):
+    x = x.astype(np.float32)
+    var = np.mean(x * x, axis=-1, keepdims=True, dtype=np.float32)
+    return (x * (1.0 / np.sqrt(var + np.float32(eps)))).astype(np.float32) * w.astype(np.float32)
+
+
+@pytest.mark.parametrize("M,d", [(1, 128), (7, 1024), (1000, 1024), (33, 1536), (5, 4)])
+def test_rmsnorm_matches_numpy(M, d):
+    """p3/p9: fp32 statistics, fp16 (saturating) operand out, optional fp32 copy; rows longer than 1024 take the
+    re-read path of the kernel."""
+    lib = _lib.load()
+    rng = np.random.default_rng(M + d)
+    h = (rng.standard_normal((M, d), dtype=np.float32) * rng.uniform(0.1, 300.0, (M, 1)).astype(np.float32))
+    w = (1.0 + 0.1 * rng.standard_normal(d, dtype=np.float32)).astype(np.float32)
+    xn = np.zeros((M, d), np.float16)
+    f32 = np.zeros((M, d), np.float32)
+    _lib.check(lib.p5_dbg_rmsnorm(0, None, None, 0, h.ctypes.data, w.ctypes.data, 1e-6, M, d, None, xn.ctypes.data,
+                                  f32.ctypes.data))
+    ref = _rmsnorm_ref(h, w, 1e-6)
+    np.testing.assert_allclose(f32, ref, rtol=2e-6, atol=1e-6)
+    np.testing.assert_array_equal(xn, f32.astype(np.float16))  # the fp16 operand is the RNE rounding of the fp32 value
+
+
+def test_rmsnorm_saturates_to_fp16_range():
+    lib = _lib.load()
+    h = np.zeros((2, 128), np.float32)
+    h[0, 0], h[1, :] = 1.0, 1.0
+    w = np.full(128, 1e5, np.float32)  # |rmsnorm * w| far beyond 65504 in row 0
+    xn = np.zeros((2, 128), np.float16)
+    _lib.check(lib.p5_dbg_rmsnorm(0, None, None, 0, h.ctypes.data, w.ctypes.data, 1e-6, 2, 128, None, xn.ctypes.data, None))
+    assert np.isfinite(xn.astype(np.float32)).all() and xn[0, 0] == np.float16(65504) and xn[0, 1] == 0
+
+
+def test_embed_rmsnorm_matches_numpy():
+    """p2 + p3 of layer 0: gather of the fp16 embedding rows into the fp32 residual stream, then the norm;
+    ids outside the vocabulary read row 0 (defensive: the tokenizer LUT never emits them)."""
+    lib = _lib.load()
+    rng = np.random.default_rng(4)
+    V, d, M = 150, 1024, 777
+    embd = (rng.standard_normal((V, d), dtype=np.float32) * 0.7).astype(np.float16)
+    ids = rng.integers(0, V, M).astype(np.int32)
+    ids[5], ids[6] = -3, V + 9
+    w = (1.0 + 0.1 * rng.standard_normal(d, dtype=np.float32)).astype(np.float32)
+    h = np.zeros((M, d), np.float32)
+    xn = np.zeros((M, d), np.float16)
+    _lib.check(lib.p5_dbg_rmsnorm(0, ids.ctypes.data, embd.ctypes.data, V, None, w.ctypes.data, 1e-6, M, d,
+                                  h.ctypes.data, xn.ctypes.data, None))
+    safe = np.where((ids < 0) | (ids >= V), 0, ids)
+    np.testing.assert_array_equal(h, embd[safe].astype(np.float32))
+    ref = _rmsnorm_ref(h, w, 1e-6)
+    assert np.abs(xn.astype(np.float32) - ref).max() < 2e-3 * max(1.0, np.abs(ref).max())
+
+
+def _head_ref(taps, cu, b0, w1, b1, include_eos):
+    c1, ncls, ks = w1.shape[1], w1.shape[0], w1.shape[2]
+    pad = ks // 2
+    logits = []
+    for s in range(len(cu) - 1):
+        tok0, T = int(cu[s]), int(cu[s + 1] - cu[s])
+        L = T - 2
+        R = L + 1 if include_eos else L
+        rows = taps[tok0 + 1:tok0 + 1 + R].reshape(R, ks, c1)  # [head row, tap, channel]
+        y = np.zeros((R + 2 * pad, c1), np.float32)
+        for r in range(R):
+            acc = b0.copy()
+            for t in range(ks):
+                src = r + t - pad
+                if 0 <= src < R:
+                    acc += rows[src, t]
+            y[r + pad] = np.maximum(acc, 0.0)
+        z = np.tile(b1, (L, 1)).astype(np.float32)
+        for t in range(ks):
+            z += y[t:t + L] @ w1[:, :, t].T
+        logits.append(z)
+    return np.concatenate(logits)
+
+
+@pytest.mark.parametrize("include_eos", [1, 0])
+def test_head_matches_numpy(include_eos):
+    """p10 + p11: shifted tap sum with per-sequence zero padding (never a neighbour's rows), ReLU, second conv,
+    20-way arg-max with ties to the lowest class; chunk boundaries at 64 residues."""
+    lib = _lib.load()
+    rng = np.random.default_rng(8)
+    lens = [1, 2, 3, 63, 64, 65, 130, 300, 7]
+    cu = np.zeros(len(lens) + 1, np.int32)
+    cu[1:] = np.cumsum([L + 2 for L in lens])
+    M, c1, ncls, ks = int(cu[-1]), 32, 20, 7
+    taps = rng.standard_normal((M, ks * c1), dtype=np.float32)
+    b0 = rng.standard_normal(c1, dtype=np.float32) * 0.1
+    w1 = rng.standard_normal((ncls, c1, ks), dtype=np.float32) * 0.2
+    b1 = rng.standard_normal(ncls, dtype=np.float32) * 0.1
+    n_res = sum(lens)
+    letters = np.zeros(n_res, np.uint8)
+    logits = np.zeros((n_res, ncls), np.float32)
+    _lib.check(lib.p5_dbg_head(0, taps.ctypes.data, cu.ctypes.data, len(lens), b0.ctypes.data, w1.ctypes.data,
+                               b1.ctypes.data, c1, ncls, ks, include_eos, letters.ctypes.data, logits.ctypes.data))
+    ref = _head_ref(taps, cu, b0, w1, b1, bool(include_eos))
+    assert np.abs(logits - ref).max() < 1e-4
+    alphabet = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
+    np.testing.assert_array_equal(letters, alphabet[np.argmax(logits, -1)])  # arg-max of the kernel's own logits
+    srt = np.sort(ref, -1)
+    decided = (srt[:, -1] - srt[:, -2]) > 1e-3
+    np.testing.assert_array_equal(letters[decided], alphabet[np.argmax(ref, -1)][decided])
+
+
+def test_head_argmax_ties_go_to_the_lowest_class():
+    lib = _lib.load()
+    cu = np.array([0, 12], np.int32)  # one sequence of 10 residues
+    c1, ncls, ks = 32, 20, 7
+    taps = np.zeros((12, ks * c1), np.float32)
+    b0, w1 = np.zeros(c1, np.float32), np.zeros((ncls, c1, ks), np.float32)
+    b1 = np.zeros(ncls, np.float32)
+    b1[[4, 11, 17]] = 2.5  # three classes tie at the top everywhere
+    letters = np.zeros(10, np.uint8)
+    _lib.check(lib.p5_dbg_head(0, taps.ctypes.data, cu.ctypes.data, 1, b0.ctypes.data, w1.ctypes.data, b1.ctypes.data,
+                               c1, ncls, ks, 1, letters.ctypes.data, None))
+    assert letters.tobytes() == b"F" * 10  # "ACDEFGHIKLMNPQRSTVWY"[4]

@@ -69,6 +69,8 @@ def _bind_optional(lib: C.CDLL) -> None:
         "p5_encode_debug": (C.c_int, [vp, vp, C.c_uint32, vp, vp, vp]),
         "p5_get_stats": (C.c_int, [vp, f64p, C.c_int]),
         "p5_dbg_attention": (C.c_int, [C.c_int, C.c_int, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_int, f32p]),
+        "p5_dbg_rmsnorm": (C.c_int, [C.c_int, vp, vp, C.c_uint32, vp, vp, C.c_float, C.c_uint32, C.c_uint32, vp, vp, vp]),
+        "p5_dbg_head": (C.c_int, [C.c_int, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp, vp]),
         "p5_dbg_partition_probe": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, f32p]),
     }
     for name, (res, args) in sigs.items():

@@ -209,4 +209,74 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
     });
 }
 
+extern "C" int p5_dbg_rmsnorm(int device, const int32_t* ids_host, const uint16_t* embd_host, uint32_t n_vocab,
+                              const float* h_host, const float* w_host, float eps, uint32_t M, uint32_t d,
+                              float* h_out_host, uint16_t* xn_host, float* f32_host) {
+    return guarded([&] {
+        P5_REQUIRE(w_host && xn_host && M >= 1 && d >= 4 && d % 4 == 0, P5_ERR_ARG, "bad argument");
+        const bool embed = ids_host != nullptr;
+        P5_REQUIRE(embed ? (embd_host && n_vocab >= 1 && h_out_host) : (h_host != nullptr), P5_ERR_ARG, "null buffer");
+        P5_CUDA(cudaSetDevice(device));
+        ScratchBuf h(size_t(M) * d * 4), w(size_t(d) * 4), xn(size_t(M) * d * 2), f32(size_t(M) * d * 4),
+            ids(size_t(M) * 4), embd(embed ? size_t(n_vocab) * d * 2 : 0);
+        P5_CUDA(cudaMemcpy(w.p, w_host, size_t(d) * 4, cudaMemcpyHostToDevice));
+        cudaStream_t st;
+        P5_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        if (embed) {
+            P5_CUDA(cudaMemcpy(ids.p, ids_host, size_t(M) * 4, cudaMemcpyHostToDevice));
+            P5_CUDA(cudaMemcpy(embd.p, embd_host, size_t(n_vocab) * d * 2, cudaMemcpyHostToDevice));
+            launch_embed_rmsnorm(st, static_cast<const int32_t*>(ids.p), static_cast<const __half*>(embd.p),
+                                 static_cast<const float*>(w.p), eps, static_cast<float*>(h.p), static_cast<__half*>(xn.p),
+                                 M, d, n_vocab);
+        } else {
+            P5_CUDA(cudaMemcpy(h.p, h_host, size_t(M) * d * 4, cudaMemcpyHostToDevice));
+            launch_rmsnorm(st, static_cast<const float*>(h.p), static_cast<const float*>(w.p), eps,
+                           static_cast<__half*>(xn.p), f32_host ? static_cast<float*>(f32.p) : nullptr, M, d);
+        }
+        P5_CUDA(cudaStreamSynchronize(st));
+        cudaStreamDestroy(st);
+        P5_CUDA(cudaMemcpy(xn_host, xn.p, size_t(M) * d * 2, cudaMemcpyDeviceToHost));
+        if (embed) P5_CUDA(cudaMemcpy(h_out_host, h.p, size_t(M) * d * 4, cudaMemcpyDeviceToHost));
+        else if (f32_host) P5_CUDA(cudaMemcpy(f32_host, f32.p, size_t(M) * d * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+extern "C" int p5_dbg_head(int device, const float* taps_host, const int32_t* cu_host, uint32_t n_seq, const float* b0_host,
+                           const float* w1_host, const float* b1_host, uint32_t c1, uint32_t n_cls, uint32_t ksize,
+                           int include_eos, uint8_t* letters_host, float* logits_host) {
+    return guarded([&] {
+        P5_REQUIRE(taps_host && cu_host && b0_host && w1_host && b1_host && letters_host && n_seq >= 1, P5_ERR_ARG,
+                   "null buffer");
+        P5_CUDA(cudaSetDevice(device));
+        const uint32_t M = uint32_t(cu_host[n_seq]);
+        std::vector<int2> work;
+        size_t n_res = 0;
+        for (uint32_t s = 0; s < n_seq; ++s) {
+            const int T = cu_host[s + 1] - cu_host[s];
+            P5_REQUIRE(T >= 3, P5_ERR_ARG, "sequence %u has %d tokens (prefix + >= 1 residue + </s>)", s, T);
+            for (int r = 0; r < T - 2; r += int(kHeadChunk)) work.push_back(make_int2(int(s), r));
+            n_res += size_t(T - 2);
+        }
+        const size_t taps_n = size_t(M) * ksize * c1;
+        ScratchBuf taps(taps_n * 4), cu((n_seq + 1) * 4), wk(work.size() * sizeof(int2)), b0(size_t(c1) * 4),
+            w1(size_t(n_cls) * c1 * ksize * 4), b1(size_t(n_cls) * 4), letters(n_res), logits(n_res * n_cls * 4);
+        P5_CUDA(cudaMemcpy(taps.p, taps_host, taps_n * 4, cudaMemcpyHostToDevice));
+        P5_CUDA(cudaMemcpy(cu.p, cu_host, (n_seq + 1) * 4, cudaMemcpyHostToDevice));
+        P5_CUDA(cudaMemcpy(wk.p, work.data(), work.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        P5_CUDA(cudaMemcpy(b0.p, b0_host, size_t(c1) * 4, cudaMemcpyHostToDevice));
+        P5_CUDA(cudaMemcpy(w1.p, w1_host, size_t(n_cls) * c1 * ksize * 4, cudaMemcpyHostToDevice));
+        P5_CUDA(cudaMemcpy(b1.p, b1_host, size_t(n_cls) * 4, cudaMemcpyHostToDevice));
+        cudaStream_t st;
+        P5_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        launch_head(st, static_cast<const float*>(taps.p), static_cast<const int32_t*>(cu.p),
+                    static_cast<const int2*>(wk.p), uint32_t(work.size()), static_cast<const float*>(b0.p),
+                    static_cast<const float*>(w1.p), static_cast<const float*>(b1.p), c1, n_cls, ksize, include_eos,
+                    static_cast<uint8_t*>(letters.p), logits_host ? static_cast<float*>(logits.p) : nullptr);
+        P5_CUDA(cudaStreamSynchronize(st));
+        cudaStreamDestroy(st);
+        P5_CUDA(cudaMemcpy(letters_host, letters.p, n_res, cudaMemcpyDeviceToHost));
+        if (logits_host) P5_CUDA(cudaMemcpy(logits_host, logits.p, n_res * n_cls * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
 extern "C" const char* p5_last_error(void) { return p5::last_error_cstr(); }
