@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-seqs", type=int, default=3)
+    ap.add_argument("--attn-impl", type=int, default=-1, help="A/B: library option attn_impl (default: the library's)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -224,6 +225,8 @@ def main():
 
     pred = Predictor(MODEL_DIR, devices=[local_rank])
     pred.set_option("profile", 1)
+    if args.attn_impl >= 0:
+        pred.set_option("attn_impl", args.attn_impl)
     pred.stage(aa, off)
     for _ in range(args.warmup):
         pred.run_staged(None)

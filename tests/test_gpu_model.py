@@ -1,9 +1,13 @@
 """End-to-end parity of the CUDA path (through the C ABI) against the oracle, on the B200.
 
 Parity bar (stated in DESIGN.md): encoder output and logits within the fp16-policy tolerances below;
-3Di letters identical to the oracle's wherever the oracle's top-2 logit margin exceeds the logit
-tolerance (a smaller margin can legitimately flip under a different fp32 summation order), and the
-CUDA path itself bit-identical across batchings, devices and runs.
+3Di letters IDENTICAL to the oracle's - zero mismatches - wherever the oracle's top-2 logit margin exceeds twice
+the logit tolerance (a smaller margin can legitimately flip under a different fp32 summation order: the two CPU
+oracles, numpy and C, differ from each other by 1.3e-2 in the logits at full size); the residues under the margin
+are counted and printed, never waved through silently.  The CUDA path itself is bit-identical across batchings,
+devices and runs.  Full-size pins: tests/golden/hf_t5_full.npz (HF T5EncoderModel fp32, 24 layers) and
+tests/golden/oracle_letters_full.npz (oracle letters + margins of all 256 config-2 sequences, 64 ragged config-4
+sequences and one 3,946-aa config-5 sequence).
 """
 import os
 
@@ -18,8 +22,12 @@ from unicore_b200.predictor import Predictor, pack_sequences
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "hf_t5_tiny.npz")
+GOLDEN_FULL = os.path.join(os.path.dirname(__file__), "golden", "hf_t5_full.npz")
+LETTERS_FULL = os.path.join(os.path.dirname(__file__), "golden", "oracle_letters_full.npz")
 TINY_HID_TOL, TINY_LOGIT_TOL = 1e-3, 1e-2
-FULL_HID_TOL, FULL_LOGIT_TOL = 4e-2, 8e-2
+# full size, 24 layers: measured GPU vs oracle 8.6e-3 (hidden) / 1.7e-2 (logits); C oracle vs numpy oracle 5.2e-3 / 1.3e-2
+FULL_HID_TOL, FULL_LOGIT_TOL = 2e-2, 2.5e-2
+LETTER_MARGIN = 2 * FULL_LOGIT_TOL  # letters must be identical wherever the oracle's top-2 margin exceeds this
 
 
 def _check_against_oracle(pred, om, seq, hid_tol, logit_tol):
@@ -29,10 +37,24 @@ def _check_against_oracle(pred, om, seq, hid_tol, logit_tol):
     assert np.abs(logits - ologits).max() < logit_tol
     got, want = np.frombuffer(letters, np.uint8), np.frombuffer(ol, np.uint8)
     decided = O.top2_margin(ologits) > 2 * logit_tol
-    assert (got[decided] == want[decided]).all()
+    assert (got[decided] == want[decided]).all()  # ZERO mismatches above the margin
     # the GPU letters are the arg-max of the GPU logits (ties -> lowest index)
     assert letters == O.THREE_DI[np.argmax(logits, -1)].tobytes()
-    return int((got != want).sum()), len(seq)
+    print(f"L={len(seq)}: hidden maxdiff {np.abs(hid - ohid).max():.2e}, logit maxdiff {np.abs(logits - ologits).max():.2e}, "
+          f"{int((~decided).sum())} residues under the margin {2 * logit_tol}, {int((got != want).sum())} of them differ")
+    return int((got != want).sum()), int((~decided).sum())
+
+
+def _check_letters(got: np.ndarray, want: np.ndarray, margin: np.ndarray, tag: str):
+    """0 mismatches where the oracle's top-2 margin exceeds LETTER_MARGIN; the rest is counted and printed."""
+    assert got.shape == want.shape == margin.shape
+    decided = margin > LETTER_MARGIN
+    bad = (got != want)
+    print(f"{tag}: {len(got)} residues, {int((~decided).sum())} under the margin {LETTER_MARGIN} "
+          f"({int((bad & ~decided).sum())} of them differ), {int((bad & decided).sum())} mismatches above it; "
+          f"largest margin of a differing residue {float(margin[bad].max()) if bad.any() else 0.0:.4f}")
+    assert not (bad & decided).any(), f"{tag}: {int((bad & decided).sum())} letters differ above the margin"
+    return int(bad.sum())
 
 
 @pytest.fixture(scope="module")
@@ -186,19 +208,66 @@ def full(full_dir):
 
 def test_full_size_matches_oracle(full, full_oracle):
     rng = np.random.default_rng(21)
-    mism = total = 0
     for L in (30, 350):
-        a, b = _check_against_oracle(full, full_oracle, random_protein(rng, L), FULL_HID_TOL, FULL_LOGIT_TOL)
-        mism, total = mism + a, total + b
-    assert mism <= 0.02 * total
+        mism, under = _check_against_oracle(full, full_oracle, random_protein(rng, L), FULL_HID_TOL, FULL_LOGIT_TOL)
+        assert mism <= under  # only residues under the margin may differ (asserted to be none above it)
 
 
 def test_full_size_long_sequence(full, full_oracle):
     """1,200 residues: more than the 1024-token split default of Foldseek, 19 key tiles per query tile, far
     off-diagonal tiles on both sides (constant-bias path) and several lazy rescales of the accumulator."""
     rng = np.random.default_rng(22)
-    a, b = _check_against_oracle(full, full_oracle, random_protein(rng, 1200), FULL_HID_TOL, FULL_LOGIT_TOL)
-    assert a <= 0.02 * b
+    mism, under = _check_against_oracle(full, full_oracle, random_protein(rng, 1200), FULL_HID_TOL, FULL_LOGIT_TOL)
+    assert mism <= under
+
+
+def test_full_size_matches_hf_golden(full):
+    """24 layers deep against the independent implementation: HF T5EncoderModel (fp32, CPU) + torch Conv1d on the same
+    synthetic weights (tests/golden/make_hf_golden.py full).  The difference is the fp16 policy of the path (fp16 GEMM
+    operands, saturation, fp16 P, ex2.approx): the C oracle with the same policy sits 6.6e-3 / 1.9e-2 from HF."""
+    g = np.load(GOLDEN_FULL)
+    step = int(g["row_step"])
+    for n, s in enumerate(g["seqs"]):
+        hid, logits, letters = full.encode_debug(s.encode())
+        dh = np.abs(hid[::step] - g[f"full_hidden_{n}"]).max()
+        dl = np.abs(logits - g[f"full_logits_{n}"]).max()
+        want = O.THREE_DI[np.argmax(g[f"full_logits_{n}"], -1)]
+        margin = O.top2_margin(g[f"full_logits_{n}"])
+        print(f"HF golden {n} (L={len(s)}): hidden maxdiff {dh:.2e}, logit maxdiff {dl:.2e}")
+        assert dh < 2.5e-2 and dl < 5e-2
+        decided = margin > 0.1
+        got = np.frombuffer(letters, np.uint8)
+        assert (got[decided] == want[decided]).all()
+
+
+def test_config2_letters_match_the_oracle_fixture(full):
+    """ALL 256 sequences of BASELINE config 2 against the committed oracle letters (not one sample)."""
+    f = np.load(LETTERS_FULL)
+    aa, off = spec.synthetic_proteome("config2")
+    got = full.predict_packed(aa, off)
+    _check_letters(got, f["config2_letters"], f["config2_margin"], "config 2 (256 x 350 aa)")
+
+
+def test_config4_letters_match_the_oracle_fixture(full):
+    """64 ragged config-4 sequences (64..1024 aa) in one packed batch against the committed oracle letters."""
+    f = np.load(LETTERS_FULL)
+    aa, off = spec.synthetic_proteome("config4", n=int(f["config4_n"]))
+    got = full.predict_packed(aa, off)
+    _check_letters(got, f["config4_letters"], f["config4_margin"], "config 4 (first 64 sequences)")
+
+
+def test_config5_long_sequence_matches_the_oracle_fixture(full):
+    """One 3,946-aa config-5 sequence, full-length attention (split_len 0), against the committed oracle letters; and
+    the same sequence inside a batch of other long sequences gives the same bytes."""
+    f = np.load(LETTERS_FULL)
+    aa, off = spec.synthetic_proteome("config5", n=int(f["config5_n"]))
+    i = int(f["config5_index"])
+    seq = aa[int(off[i]):int(off[i + 1])].tobytes()
+    got = np.frombuffer(full.predict([seq], split_len=0)[0], np.uint8)
+    _check_letters(got, f["config5_letters"], f["config5_margin"], f"config 5 (sequence {i}, {len(seq)} aa)")
+    lo = max(0, i - 2)
+    batch = [aa[int(off[k]):int(off[k + 1])].tobytes() for k in range(lo, lo + 5)]
+    assert full.predict(batch, split_len=0)[i - lo] == got.tobytes()
 
 
 def test_config2_properties(full):

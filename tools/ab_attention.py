@@ -4,7 +4,8 @@
 
 Shapes: config 2 (256 x 352 tokens x 32 heads), a config-4-like ragged mix and a config-5-like long mix.
 impl 16 + f runs feature mask f (1 = TMA-fetched bias table, 2 = deferred epilogue + item-spanning MMA stream,
-4 = TMA-store epilogue, 8 = one tcgen05.commit per event); impl 0 is the mma.sync kernel.  Every variant is also compared bit for bit with mask 0.
+4 = TMA-store epilogue, 8 = one tcgen05.commit per event); impl 2 is the second-generation kernel (two softmax
+warpgroups per item, attention_tc2.cu); impl 0 is the mma.sync kernel.  Every variant is also compared bit for bit with mask 0.
 """
 import argparse
 import ctypes as C
@@ -34,27 +35,33 @@ def main():
     a = ap.parse_args()
     lib = _lib.load()
     rng = np.random.default_rng(0)
+    # (token counts, scale of the random q/k/v): scale 0.6 gives small un-scaled scores (the lazy rescale of the
+    # accumulator almost never fires), scale 3.0 gives |q.k| up to ~1000 as trained T5 weights can (rescales are timed)
     shapes = {
-        "config2 256x352": [352] * 256,
-        "config4-like 280 seqs 66..1026": [int(x) + 2 for x in np.clip(np.round(rng.lognormal(np.log(260), 0.65, 280)), 64, 1024)],
-        "config5-like 30 seqs 2002..4002": [int(x) + 2 for x in rng.integers(2000, 4001, 30)],
+        "config2 256x352": ([352] * 256, 0.6),
+        "config2 256x352 peaked (x3.0)": ([352] * 256, 3.0),
+        "config4-like 280 seqs 66..1026": ([int(x) + 2 for x in np.clip(np.round(rng.lognormal(np.log(260), 0.65, 280)), 64, 1024)], 0.6),
+        "config5-like 30 seqs 2002..4002": ([int(x) + 2 for x in rng.integers(2000, 4001, 30)], 0.6),
+        "config5-like peaked (x3.0)": ([int(x) + 2 for x in rng.integers(2000, 4001, 30)], 3.0),
     }
     H = 32
     res = {}
-    for name, lens in shapes.items():
+    for name, (lens, scale) in shapes.items():
         cu = np.zeros(len(lens) + 1, np.int32)
         cu[1:] = np.cumsum(lens)
         M = int(cu[-1])
-        qkv = (rng.standard_normal((M, 3 * H * 128), dtype=np.float32) * 0.6).astype(np.float16)
+        qkv = (rng.standard_normal((M, 3 * H * 128), dtype=np.float32) * scale).astype(np.float16)
         bias = (rng.standard_normal((H, 257), dtype=np.float32) * 0.5).astype(np.float32)
         flops = 4.0 * 128 * H * float(sum(t * t for t in lens))
         base = None
         row = {}
-        for impl in (16, 17, 18, 20, 23, 31, 0):
+        for impl in (16, 31, 2, 0):
             ctx, ms = run(lib, impl, qkv, cu, H, bias, a.iters)
             if base is None:
                 base = ctx
-            same = bool(np.array_equal(ctx.view(np.uint16), base.view(np.uint16))) if impl else None
+            same = bool(np.array_equal(ctx.view(np.uint16), base.view(np.uint16))) if impl >= 16 else None
+            if impl == 2:  # different summation order of the row sums: compare within fp16 noise
+                row["impl2_maxdiff_vs_mask0"] = float(np.abs(ctx.astype(np.float32) - base.astype(np.float32)).max())
             row["impl%d" % impl] = {"ms": ms, "tflops": flops / ms * 1e-9, "bit_identical_to_mask0": same}
             print("%-34s impl %2d  %.3f ms  %6.1f TFLOP/s  same=%s" % (name, impl, ms, flops / ms * 1e-9, same), flush=True)
         res[name] = {"tokens": M, "flops": flops, "variants": row}

@@ -75,7 +75,7 @@ extern "C" int p5_set_option(p5_model* h, const char* key, int64_t value) {
                 model_rebuild_weight_maps(*h->m);
             }
         } else if (k == "attn_impl") {
-            P5_REQUIRE(value == 0 || value == 1, P5_ERR_ARG, "attn_impl must be 0 (mma.sync) or 1 (tcgen05)");
+            P5_REQUIRE(value >= 0 && value <= 2, P5_ERR_ARG, "attn_impl must be 0 (mma.sync), 1 (tcgen05, first kernel) or 2 (tcgen05, two softmax warpgroups)");
             o.attn_impl = int(value);
         } else if (k == "profile") {
             o.profile = value != 0;

@@ -141,9 +141,11 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         P5_CUDA(cudaSetDevice(device));
         attention_init_device();
         attention_tc_init_device();
-        // impl 16 + f = tcgen05 kernel with feature mask f (attention_tc.cu), for A/B tests of the pipelining features
-        P5_REQUIRE(impl == 0 || impl == 1 || (impl >= 16 && impl < 32), P5_ERR_ARG,
-                   "impl must be 0 (mma.sync), 1 (tcgen05) or 16..31 (tcgen05 with an explicit feature mask)");
+        attention_tc2_init_device();
+        // impl 2 = second-generation tcgen05 kernel (two softmax warpgroups per item); impl 16 + f = tcgen05 kernel with feature mask f (attention_tc.cu), for A/B tests of the pipelining features
+        P5_REQUIRE((impl >= 0 && impl <= 2) || (impl >= 16 && impl < 32), P5_ERR_ARG,
+                   "impl must be 0 (mma.sync), 1 (tcgen05), 2 (tcgen05, two softmax warpgroups) or 16..31 (first tcgen05 "
+                   "kernel with an explicit feature mask)");
         const int features = impl >= 16 ? impl - 16 : -1;
         cudaDeviceProp prop;
         P5_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -177,6 +179,12 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         cudaStream_t st;
         P5_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         auto run = [&] {
+            if (impl == 2) {
+                launch_attention_tc2(st, prop.multiProcessorCount, tm_q, tm_kv, static_cast<__half*>(ctx.p),
+                                     static_cast<const int4*>(wk4.p), uint32_t(work4.size()),
+                                     static_cast<const float*>(e_ext.p), n_head, max_dist);
+                return;
+            }
             if (impl >= 1) {
                 launch_attention_tc(st, prop.multiProcessorCount, tm_q, tm_kv, tm_ctx, static_cast<__half*>(ctx.p),
                                     static_cast<const int4*>(wk4.p), uint32_t(work4.size()),

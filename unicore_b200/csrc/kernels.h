@@ -41,6 +41,12 @@ void launch_attention_tc(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, 
                          const CUtensorMap& tm_ctx, __half* ctx, const int4* work128, uint32_t n_work,
                          const float* e_ext, uint32_t H, uint32_t max_dist, int features = -1);
 
+// Second-generation tcgen05 kernel (attention_tc2.cu, the product default): two softmax warpgroups per item taking
+// the key tiles alternately, last key tile at its real width, direct 32-byte stores of ctx (no store descriptor).
+void attention_tc2_init_device();
+void launch_attention_tc2(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, const CUtensorMap& tm_kv, __half* ctx,
+                          const int4* work128, uint32_t n_work, const float* e_ext, uint32_t H, uint32_t max_dist);
+
 constexpr uint32_t kAttnBlockM = 64;  // query rows per attention work item
 constexpr uint32_t kHeadChunk = 64;   // residues per head work item
 constexpr uint32_t kHeadDim = 128;    // the attention kernel is specialised on ProstT5's d_kv

@@ -349,6 +349,7 @@ void DeviceCtx::init(int device, const Model* m) {
     gemm_init_device();
     attention_init_device();
     attention_tc_init_device();
+    attention_tc2_init_device();
 }
 
 void DeviceCtx::load_weights(const GgufFile& g) {
@@ -580,7 +581,9 @@ void DeviceCtx::forward(const MetaLayout& l, const int32_t* meta_d, uint8_t* let
         const LayerW& L = layers[i];
         gemm(Epi::StoreF16, tm_xn, L.tm_qkv, qkv.p, 3 * inner, d);
         prof_begin(PC_ATTN);
-        if (opt.attn_impl == 1 && e_ext)
+        if (opt.attn_impl == 2 && e_ext)
+            launch_attention_tc2(stream, num_sms, tm_q, tm_kv, ctx.as<__half>(), aw128, l.n_aw128, e_ext, hp.n_head, hp.max_distance);
+        else if (opt.attn_impl == 1 && e_ext)
             launch_attention_tc(stream, num_sms, tm_q, tm_kv, tm_ctx_st, ctx.as<__half>(), aw128, l.n_aw128, e_ext, hp.n_head,
                                 hp.max_distance);
         else
