@@ -101,6 +101,34 @@ int p5_encode_debug(p5_model* m, const uint8_t* aa, uint32_t len, float* hidden_
  *  [8] attention ms  [9] attention FLOPs  [10] norm+embed ms  [11] head ms  [12] H2D bytes  [13] D2H bytes */
 int p5_get_stats(const p5_model* m, double* out, int n);
 
+/* ---- one process per GPU (north_star: "sharded by count across the 8 GPUs of one box, with a single NCCL all-gather
+ * over NVLink of the emitted 3Di byte strings before the DB write").  The reference delegates multi-GPU to the child
+ * process through CUDA_VISIBLE_DEVICES [REF README.md:142-145]; here every rank loads the model on its own device,
+ * predicts its count-shard and takes part in ONE ncclAllGather.  NCCL is bound at run time (libnccl.so.2) when the
+ * first of these functions is called; the single-GPU functions above never touch it.
+ *
+ *   p5_comm_unique_id   rank 0 creates the 128-byte NCCL id and hands it to the other ranks by any side channel
+ *                       (a pipe from the parent process in `unicore-b200 createdb --procs N`, a broadcast in bench.py)
+ *   p5_comm_create      ncclCommInitRank on `device`; may run on a thread of its own while p5_model_load reads the
+ *                       weights (communicator set-up is ~0.4 s and would otherwise sit behind the prediction)
+ *   p5_shard_indices    the shard of `rank`: sequences sorted longest first (stable), dealt in snake order
+ *                       0..W-1,W-1..0 (equal counts +-1, near-equal cost).  Pure host arithmetic on the lengths, so
+ *                       every rank knows every shard and no length table is exchanged.  idx_out holds n_seq entries.
+ *   p5_allgather_3di    local = this rank's letters packed in shard order -> out_all = the letters of ALL sequences
+ *                       at `offsets` (input order), on every rank
+ *   p5_predict_sharded  the whole step: every rank passes the WHOLE proteome (same arguments as p5_predict); the
+ *                       library predicts the rank's shard and all-gathers.  comm == NULL or a world of 1 = p5_predict. */
+#define P5_COMM_ID_BYTES 128
+typedef struct p5_comm p5_comm;
+int p5_comm_unique_id(uint8_t* id128);
+int p5_comm_create(const uint8_t* id128, int rank, int world, int device, p5_comm** out);
+void p5_comm_free(p5_comm* c);
+int p5_comm_info(const p5_comm* c, int* rank, int* world, int* nccl_version);
+int p5_shard_indices(const uint64_t* offsets, uint64_t n_seq, int rank, int world, uint64_t* idx_out, uint64_t* n_out);
+int p5_allgather_3di(p5_comm* c, const uint8_t* local, const uint64_t* offsets, uint64_t n_seq, uint8_t* out_all);
+int p5_predict_sharded(p5_model* m, p5_comm* c, const uint8_t* aa, const uint64_t* offsets, uint64_t n_seq,
+                       uint8_t* out_3di, uint32_t split_len);
+
 const char* p5_last_error(void);
 
 #ifdef __cplusplus

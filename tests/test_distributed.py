@@ -1,4 +1,5 @@
-"""Sharding + the 3Di all-gather on 2 CPU ranks (gloo): the host-side logic of the N>1 path."""
+"""Sharding + the 3Di all-gather on 2 CPU ranks (gloo): the host-side logic of the N>1 path, and the library's own
+count-sharding (csrc/comm.cc, pure host arithmetic) against its Python mirror."""
 import os
 import socket
 import subprocess
@@ -25,8 +26,7 @@ def test_shards_partition_and_balance():
 
 
 def test_scatter_shards_restores_input_order():
-    """Shard order (length-sorted, snake-dealt) -> input order, for every world size including 1 (the single-rank
-    createdb_dist run writes the DB in input order, not in the planner's order)."""
+    """Shard order (length-sorted, snake-dealt) -> input order, for every world size including 1."""
     aa, off = spec.synthetic_proteome("config4", n=200)
     lens = (off[1:] - off[:-1]).astype(np.int64)
     want = ((aa.astype(np.int32) * 7 + 3) % 20 + 65).astype(np.uint8)
@@ -38,12 +38,32 @@ def test_scatter_shards_restores_input_order():
         np.testing.assert_array_equal(D.scatter_shards(rows, lens, off), want)
 
 
+def test_native_sharding_equals_python_mirror():
+    """p5_shard_indices (what p5_predict_sharded and `unicore-b200 createdb --procs N` use) == distributed.shard_indices."""
+    from unicore_b200.predictor import shard_indices_native
+    rng = np.random.default_rng(0)
+    for n, world in ((0, 1), (1, 2), (7, 3), (1000, 8), (257, 4), (5000, 8)):
+        lens = rng.integers(0, 50, n) if n != 5000 else spec.synthetic_lengths("config4", n=5000)
+        off = np.zeros(n + 1, np.uint64)
+        off[1:] = np.cumsum(lens)
+        for r in range(world):
+            np.testing.assert_array_equal(shard_indices_native(off, r, world), D.shard_indices(lens, r, world))
+    from unicore_b200._lib import P5Error
+    import pytest
+    with pytest.raises(P5Error):
+        shard_indices_native(np.array([0, 5, 3], np.uint64), 0, 2)  # decreasing offsets
+    with pytest.raises(P5Error):
+        shard_indices_native(np.array([0, 5], np.uint64), 2, 2)  # rank out of range
+
+
 WORKER = r"""
 import os, sys
 import numpy as np
 sys.path.insert(0, sys.argv[1])
+sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
 import torch.distributed as dist
 from unicore_b200 import distributed as D, prostt5_spec as spec
+import gloo_harness
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 aa, off = spec.synthetic_proteome("config4", n=300)
@@ -52,7 +72,7 @@ idx = D.shard_indices(lens, rank, world)
 laa, loff = D.take_shard(aa, off, idx)
 # stand-in for the GPU prediction: a per-residue function of the input, so that placement errors show
 local = ((laa.astype(np.int32) * 7 + 3) % 20 + 65).astype(np.uint8)
-full = D.allgather_3di(local, lens, off)
+full = gloo_harness.allgather_3di(local, lens, off)
 want = ((aa.astype(np.int32) * 7 + 3) % 20 + 65).astype(np.uint8)
 assert np.array_equal(full, want), "gathered letters are misplaced"
 print("rank", rank, "ok", len(local), len(full))
@@ -72,37 +92,3 @@ def test_allgather_two_ranks_gloo(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert p.stdout.count("ok") == 2
-
-
-def test_python_db_writer_matches_format(tmp_path, tiny_dir):
-    """The rank-0 DB writer of createdb_dist produces a DB the reference's consumers accept, byte-identical to the
-    C++ writer's output for the same records."""
-    from oracle import host_oracle as H
-    from unicore_b200 import createdb_dist as CD
-    fasta = tmp_path / "combined_aa.fasta"
-    fasta.write_text(">unicore_aaaaaaaaaa\nMKTAYIAKQR\n>unicore_bbbbbbbbbb some desc\nGGGGG\nAA\n")
-    recs = CD.read_fasta_records(str(fasta))
-    assert recs == [(b"unicore_aaaaaaaaaa", b"MKTAYIAKQR"), (b"unicore_bbbbbbbbbb some desc", b"GGGGGAA")]
-    db = str(tmp_path / "db")
-    CD.write_foldseek_db(db, recs, [b"DVLVVVLCVV", b"PPPPPLL"], "combined_aa.fasta")
-    entries = H.check_foldseek_db(db)
-    assert entries == [("unicore_aaaaaaaaaa", "MKTAYIAKQR", "DVLVVVLCVV"), ("unicore_bbbbbbbbbb some desc", "GGGGGAA", "PPPPPLL")]
-    # same bytes as the C++ host writes (via the all-found custom-lookup path, which needs no GPU)
-    import subprocess
-    look = str(tmp_path / "look")
-    for suffix, rows in (("", [b"MKTAYIAKQR", b"GGGGGAA"]), ("_ss", [b"DVLVVVLCVV", b"PPPPPLL"])):
-        with open(look + suffix, "wb") as f:
-            for r in rows:
-                f.write(r + b"\n\0")
-    inp = tmp_path / "in"
-    inp.mkdir()
-    (inp / "Sp.fa").write_text(">a\nMKTAYIAKQR\n>b\nGGGGGAA\n")
-    out = tmp_path / "o" / "db"
-    p = subprocess.run([os.path.join(ROOT, "unicore_b200", "bin", "unicore-b200"), "createdb", str(inp), str(out),
-                        tiny_dir, "--custom-lookup", look, "-v", "0"], capture_output=True, text=True)
-    assert p.returncode == 0, p.stderr  # every sequence is in the lookup DB: no device needed
-    cpp = H.check_foldseek_db(str(out))
-    recs2 = [(n.encode(), a.encode()) for n, a, _ in cpp]
-    CD.write_foldseek_db(str(tmp_path / "db2"), recs2, [s.encode() for _, _, s in cpp], "combined_aa.fasta")
-    for suffix in ("", ".index", ".dbtype", "_ss", "_ss.index", "_ss.dbtype", "_h", "_h.index", "_h.dbtype", ".lookup", ".source"):
-        assert open(str(out) + suffix, "rb").read() == open(str(tmp_path / "db2") + suffix, "rb").read(), suffix

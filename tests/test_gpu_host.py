@@ -109,17 +109,45 @@ def test_custom_lookup_partial(tmp_path, tiny_dir, tiny_oracle):
     _check_ss([(H.hashed_name(s), s, entries[s]) for s in (seqs[0], seqs[2])], tiny_oracle)
 
 
-def test_createdb_dist_single_rank(tmp_path, tiny_dir, tiny_oracle):
-    """The one-process-per-GPU entry (here world size 1; the N>1 path is the gloo test + bench.py --gpus N)."""
-    import sys
-    rng = np.random.default_rng(9)
-    recs = [(H.hashed_name(s), s) for s in (random_protein(rng, int(L)).decode() for L in (12, 90, 257))]
-    fasta = tmp_path / "combined_aa.fasta"
-    fasta.write_text("".join(f">{n}\n{s}\n" for n, s in recs))
-    db = tmp_path / "db"
-    p = subprocess.run([sys.executable, "-m", "unicore_b200.createdb_dist", str(fasta), str(db), "--prostt5-model", tiny_dir,
-                        "--threads", "4", "--gpu", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
-    assert p.returncode == 0, p.stderr
-    entries = H.check_foldseek_db(str(db))
-    assert [(n, a) for n, a, _ in entries] == recs
-    _check_ss(entries, tiny_oracle)
+def test_library_comm_world_of_one(tiny_dir, tiny_oracle):
+    """The library's own NCCL path on one GPU: unique id, ncclCommInitRank (world 1), p5_allgather_3di (identity
+    placement through the padded slab) and p5_predict_sharded == p5_predict."""
+    from unicore_b200.predictor import Comm, Predictor, comm_unique_id, pack_sequences
+    rng = np.random.default_rng(19)
+    seqs = [random_protein(rng, int(L)) for L in (12, 90, 257, 5, 33)]
+    aa, off = pack_sequences(seqs)
+    comm = Comm(comm_unique_id(), 0, 1, 0)
+    assert comm.world == 1 and comm.nccl_version > 20000
+    local = ((aa.astype(np.int32) * 7 + 3) % 20 + 65).astype(np.uint8)
+    # world 1: the shard order is the length-sorted order, the gather must put every string back at its offset
+    from unicore_b200 import distributed as D
+    lens = (off[1:] - off[:-1]).astype(np.int64)
+    shard_aa, _ = D.take_shard(local, off, D.shard_indices(lens, 0, 1))
+    np.testing.assert_array_equal(comm.allgather_3di(shard_aa, off), local)
+    with Predictor(tiny_dir, devices=[0]) as p:
+        want = p.predict_packed(aa, off)
+        np.testing.assert_array_equal(p.predict_sharded(comm, aa, off), want)
+        np.testing.assert_array_equal(p.predict_sharded(None, aa, off), want)
+    comm.close()
+
+
+def test_createdb_procs_two_ranks(tmp_path, tiny_dir, tiny_oracle):
+    """`unicore-b200 createdb --procs 2`: one process per GPU, count-sharding, the library's NCCL all-gather, rank 0
+    writes the DB - byte-identical to the single-process run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.default_rng(23)
+    (tmp_path / "in").mkdir()
+    seqs = [random_protein(rng, int(L)).decode() for L in rng.integers(5, 400, 60)]
+    (tmp_path / "in" / "Sp.fa").write_text("".join(f">p{i} x\n{s}\n" for i, s in enumerate(seqs)))
+    outs = []
+    for tag, extra in (("one", ["--devices", "0"]), ("two", ["--procs", "2"])):
+        out = tmp_path / tag / "db"
+        p = subprocess.run([UNICORE, "createdb", str(tmp_path / "in"), str(out), tiny_dir, "--max-batch-tokens", "2048"] + extra,
+                           capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stdout + p.stderr
+        outs.append(str(out))
+    for suffix in ("", ".index", ".dbtype", "_ss", "_ss.index", "_ss.dbtype", "_h", "_h.index", "_h.dbtype", ".lookup"):
+        assert open(outs[0] + suffix, "rb").read() == open(outs[1] + suffix, "rb").read(), suffix
+    _check_ss(H.check_foldseek_db(outs[1]), tiny_oracle)

@@ -68,6 +68,13 @@ def _bind_optional(lib: C.CDLL) -> None:
         "p5_run_staged": (C.c_int, [vp, vp]),
         "p5_encode_debug": (C.c_int, [vp, vp, C.c_uint32, vp, vp, vp]),
         "p5_get_stats": (C.c_int, [vp, f64p, C.c_int]),
+        "p5_comm_unique_id": (C.c_int, [vp]),
+        "p5_comm_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+        "p5_comm_free": (None, [vp]),
+        "p5_comm_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "p5_shard_indices": (C.c_int, [vp, C.c_uint64, C.c_int, C.c_int, vp, C.POINTER(C.c_uint64)]),
+        "p5_allgather_3di": (C.c_int, [vp, vp, vp, C.c_uint64, vp]),
+        "p5_predict_sharded": (C.c_int, [vp, vp, vp, vp, C.c_uint64, vp, C.c_uint32]),
         "p5_dbg_attention": (C.c_int, [C.c_int, C.c_int, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_int, f32p]),
         "p5_dbg_rmsnorm": (C.c_int, [C.c_int, vp, vp, C.c_uint32, vp, vp, C.c_float, C.c_uint32, C.c_uint32, vp, vp, vp]),
         "p5_dbg_head": (C.c_int, [C.c_int, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp, vp]),

@@ -1,6 +1,9 @@
 // The drop-in C ABI (include/prostt5_b200.h): thin, exception-safe wrappers over model.cu.
 #include <cstring>
 
+#include <vector>
+
+#include "comm.h"
 #include "common.h"
 #include "model.h"
 #include "prostt5_b200.h"
@@ -9,6 +12,9 @@ using namespace p5;
 
 struct p5_model {
     Model* m;
+};
+struct p5_comm {
+    Comm* c;
 };
 
 extern "C" int p5_model_load(const char* model_dir, const int* devices, int n_devices, p5_model** out) {
@@ -75,7 +81,8 @@ extern "C" int p5_set_option(p5_model* h, const char* key, int64_t value) {
                 model_rebuild_weight_maps(*h->m);
             }
         } else if (k == "attn_impl") {
-            P5_REQUIRE(value >= 0 && value <= 2, P5_ERR_ARG, "attn_impl must be 0 (mma.sync), 1 (tcgen05, first kernel) or 2 (tcgen05, two softmax warpgroups)");
+            P5_REQUIRE(value >= 0 && value <= 3, P5_ERR_ARG,
+                       "attn_impl must be 0 (mma.sync), 1 (tcgen05, first kernel), 2 (tcgen05, two softmax warpgroups) or 3 (tcgen05, packed-pair math)");
             o.attn_impl = int(value);
         } else if (k == "profile") {
             o.profile = value != 0;
@@ -124,5 +131,87 @@ extern "C" int p5_get_stats(const p5_model* h, double* out, int n) {
                               s.class_ms[PC_GEMM], s.gemm_flops, s.class_ms[PC_ATTN], s.attn_flops,
                               s.class_ms[PC_NORM], s.class_ms[PC_HEAD], s.h2d_bytes, s.d2h_bytes};
         for (int i = 0; i < n && i < 14; ++i) out[i] = v[i];
+    });
+}
+
+// ---- one process per GPU: count-sharding + the single NCCL all-gather of the 3Di bytes (comm.cc) ----------------------
+extern "C" int p5_comm_unique_id(uint8_t* id) {
+    return guarded([&] {
+        P5_REQUIRE(id, P5_ERR_ARG, "null argument");
+        comm_unique_id(id);
+    });
+}
+
+extern "C" int p5_comm_create(const uint8_t* id, int rank, int world, int device, p5_comm** out) {
+    return guarded([&] {
+        P5_REQUIRE(id && out, P5_ERR_ARG, "null argument");
+        *out = nullptr;
+        Comm* c = new Comm(id, rank, world, device);
+        *out = new p5_comm{c};
+    });
+}
+
+extern "C" void p5_comm_free(p5_comm* h) {
+    if (!h) return;
+    try {
+        delete h->c;
+    } catch (...) {
+    }
+    delete h;
+}
+
+extern "C" int p5_comm_info(const p5_comm* h, int* rank, int* world, int* nccl_version) {
+    return guarded([&] {
+        P5_REQUIRE(h, P5_ERR_ARG, "null argument");
+        if (rank) *rank = h->c->rank;
+        if (world) *world = h->c->world;
+        if (nccl_version) *nccl_version = h->c->version;
+    });
+}
+
+extern "C" int p5_shard_indices(const uint64_t* offsets, uint64_t n_seq, int rank, int world, uint64_t* idx_out,
+                                uint64_t* n_out) {
+    return guarded([&] {
+        P5_REQUIRE(offsets && idx_out && n_out, P5_ERR_ARG, "null argument");
+        std::vector<uint64_t> lengths(n_seq);
+        for (uint64_t i = 0; i < n_seq; ++i) {
+            P5_REQUIRE(offsets[i + 1] >= offsets[i], P5_ERR_ARG, "offsets must be non-decreasing");
+            lengths[i] = offsets[i + 1] - offsets[i];
+        }
+        const std::vector<uint64_t> idx = shard_indices(lengths.data(), n_seq, rank, world);
+        for (size_t k = 0; k < idx.size(); ++k) idx_out[k] = idx[k];
+        *n_out = idx.size();
+    });
+}
+
+extern "C" int p5_allgather_3di(p5_comm* h, const uint8_t* local, const uint64_t* offsets, uint64_t n_seq, uint8_t* out_all) {
+    return guarded([&] {
+        P5_REQUIRE(h && offsets && (n_seq == 0 || out_all), P5_ERR_ARG, "null argument");
+        h->c->allgather_3di(local, offsets, n_seq, out_all);
+    });
+}
+
+extern "C" int p5_predict_sharded(p5_model* h, p5_comm* comm, const uint8_t* aa, const uint64_t* offsets, uint64_t n_seq,
+                                  uint8_t* out_3di, uint32_t split_len) {
+    return guarded([&] {
+        P5_REQUIRE(h && offsets && (n_seq == 0 || (aa && out_3di) || offsets[n_seq] == offsets[0]), P5_ERR_ARG,
+                   "null argument");
+        if (!comm || comm->c->world == 1) {
+            model_predict(*h->m, aa, offsets, n_seq, out_3di, split_len);
+            return;
+        }
+        // this rank's shard, packed in shard order
+        std::vector<uint64_t> lengths(n_seq);
+        for (uint64_t i = 0; i < n_seq; ++i) {
+            P5_REQUIRE(offsets[i + 1] >= offsets[i], P5_ERR_ARG, "offsets must be non-decreasing");
+            lengths[i] = offsets[i + 1] - offsets[i];
+        }
+        const std::vector<uint64_t> idx = shard_indices(lengths.data(), n_seq, comm->c->rank, comm->c->world);
+        std::vector<uint64_t> off(idx.size() + 1, 0);
+        for (size_t k = 0; k < idx.size(); ++k) off[k + 1] = off[k] + lengths[idx[k]];
+        std::vector<uint8_t> local_aa(off.back()), local_out(off.back());
+        for (size_t k = 0; k < idx.size(); ++k) memcpy(local_aa.data() + off[k], aa + offsets[idx[k]], lengths[idx[k]]);
+        model_predict(*h->m, local_aa.data(), off.data(), idx.size(), local_out.data(), split_len);
+        comm->c->allgather_3di(local_out.data(), offsets, n_seq, out_3di);
     });
 }

@@ -142,10 +142,11 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         attention_init_device();
         attention_tc_init_device();
         attention_tc2_init_device();
+        attention_tc3_init_device();
         // impl 2 = second-generation tcgen05 kernel (two softmax warpgroups per item); impl 16 + f = tcgen05 kernel with feature mask f (attention_tc.cu), for A/B tests of the pipelining features
-        P5_REQUIRE((impl >= 0 && impl <= 2) || (impl >= 16 && impl < 32), P5_ERR_ARG,
-                   "impl must be 0 (mma.sync), 1 (tcgen05), 2 (tcgen05, two softmax warpgroups) or 16..31 (first tcgen05 "
-                   "kernel with an explicit feature mask)");
+        P5_REQUIRE((impl >= 0 && impl <= 3) || (impl >= 16 && impl < 32), P5_ERR_ARG,
+                   "impl must be 0 (mma.sync), 1 (tcgen05), 2 (tcgen05, two softmax warpgroups), 3 (tcgen05, packed-pair math) "
+                   "or 16..31 (first tcgen05 kernel with an explicit feature mask)");
         const int features = impl >= 16 ? impl - 16 : -1;
         cudaDeviceProp prop;
         P5_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -164,6 +165,10 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         attention_tc_build_table(bias_host, n_head, max_dist, e_host.data());
         ScratchBuf e_ext(e_host.size() * 4);
         P5_CUDA(cudaMemcpy(e_ext.p, e_host.data(), e_host.size() * 4, cudaMemcpyHostToDevice));
+        std::vector<float> e2_host(size_t(n_head) * 2 * kAttnTcTable);
+        attention_tc3_build_table(bias_host, n_head, max_dist, e2_host.data());
+        ScratchBuf e_ext2(e2_host.size() * 4);
+        P5_CUDA(cudaMemcpy(e_ext2.p, e2_host.data(), e2_host.size() * 4, cudaMemcpyHostToDevice));
         ScratchBuf qkv(Mpad * 3 * inner * 2), ctx(M * inner * 2), cu((n_seq + 1) * 4), wk(work.size() * sizeof(int2)), wk4(work4.size() * sizeof(int4)),
             bias(size_t(n_head) * (2 * max_dist + 1) * 4);
         P5_CUDA(cudaMemset(qkv.p, 0, Mpad * 3 * inner * 2));
@@ -179,6 +184,12 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         cudaStream_t st;
         P5_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         auto run = [&] {
+            if (impl == 3) {
+                launch_attention_tc3(st, prop.multiProcessorCount, tm_q, tm_kv, static_cast<__half*>(ctx.p),
+                                     static_cast<const int4*>(wk4.p), uint32_t(work4.size()),
+                                     static_cast<const float*>(e_ext2.p), n_head, max_dist);
+                return;
+            }
             if (impl == 2) {
                 launch_attention_tc2(st, prop.multiProcessorCount, tm_q, tm_kv, static_cast<__half*>(ctx.p),
                                      static_cast<const int4*>(wk4.p), uint32_t(work4.size()),

@@ -47,6 +47,14 @@ void attention_tc2_init_device();
 void launch_attention_tc2(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, const CUtensorMap& tm_kv, __half* ctx,
                           const int4* work128, uint32_t n_work, const float* e_ext, uint32_t H, uint32_t max_dist);
 
+// Third tcgen05 kernel (attention_tc3.cu): the first kernel's pipeline with packed-pair fp32 math (FFMA2 / FADD2), a
+// two-copy bias table read with 64-bit loads (e_ext2 = [H][2][kAttnTcTable], attention_tc3_build_table), the last key
+// tile at its real width and direct 32-byte stores of ctx.
+void attention_tc3_init_device();
+void attention_tc3_build_table(const float* bias, uint32_t H, uint32_t max_dist, float* e_ext2);
+void launch_attention_tc3(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, const CUtensorMap& tm_kv, __half* ctx,
+                          const int4* work128, uint32_t n_work, const float* e_ext2, uint32_t H, uint32_t max_dist);
+
 constexpr uint32_t kAttnBlockM = 64;  // query rows per attention work item
 constexpr uint32_t kHeadChunk = 64;   // residues per head work item
 constexpr uint32_t kHeadDim = 128;    // the attention kernel is specialised on ProstT5's d_kv

@@ -204,7 +204,7 @@ public:
     float* out_norm = nullptr;
     __half* wc0 = nullptr;  // [K*C1, d] tap-major conv0 weight
     CUtensorMap tm_c0;
-    float *b0 = nullptr, *w1 = nullptr, *b1 = nullptr, *bias = nullptr, *e_ext = nullptr;
+    float *b0 = nullptr, *w1 = nullptr, *b1 = nullptr, *bias = nullptr, *e_ext = nullptr, *e_ext2 = nullptr;
 
     // workspace for `cap` tokens
     uint32_t cap = 0;
@@ -350,6 +350,7 @@ void DeviceCtx::init(int device, const Model* m) {
     attention_init_device();
     attention_tc_init_device();
     attention_tc2_init_device();
+    attention_tc3_init_device();
 }
 
 void DeviceCtx::load_weights(const GgufFile& g) {
@@ -440,6 +441,9 @@ void DeviceCtx::load_weights(const GgufFile& g) {
         std::vector<float> e(size_t(hp.n_head) * kAttnTcTable);
         attention_tc_build_table(m->bias_table.data(), hp.n_head, hp.max_distance, e.data());
         e_ext = upload<float>(e.data(), e.size() * 4);
+        std::vector<float> e2(size_t(hp.n_head) * 2 * kAttnTcTable);
+        attention_tc3_build_table(m->bias_table.data(), hp.n_head, hp.max_distance, e2.data());
+        e_ext2 = upload<float>(e2.data(), e2.size() * 4);
     }
     build_weight_maps();
 }
@@ -485,6 +489,7 @@ void DeviceCtx::clone_weights(const DeviceCtx& src) {
     b1 = static_cast<float*>(remap(src.b1));
     bias = static_cast<float*>(remap(src.bias));
     e_ext = static_cast<float*>(remap(src.e_ext));
+    e_ext2 = static_cast<float*>(remap(src.e_ext2));
     P5_CUDA(cudaStreamSynchronize(stream));
     build_weight_maps();
 }
@@ -581,7 +586,9 @@ void DeviceCtx::forward(const MetaLayout& l, const int32_t* meta_d, uint8_t* let
         const LayerW& L = layers[i];
         gemm(Epi::StoreF16, tm_xn, L.tm_qkv, qkv.p, 3 * inner, d);
         prof_begin(PC_ATTN);
-        if (opt.attn_impl == 2 && e_ext)
+        if (opt.attn_impl == 3 && e_ext2)
+            launch_attention_tc3(stream, num_sms, tm_q, tm_kv, ctx.as<__half>(), aw128, l.n_aw128, e_ext2, hp.n_head, hp.max_distance);
+        else if (opt.attn_impl == 2 && e_ext)
             launch_attention_tc2(stream, num_sms, tm_q, tm_kv, ctx.as<__half>(), aw128, l.n_aw128, e_ext, hp.n_head, hp.max_distance);
         else if (opt.attn_impl == 1 && e_ext)
             launch_attention_tc(stream, num_sms, tm_q, tm_kv, tm_ctx_st, ctx.as<__half>(), aw128, l.n_aw128, e_ext, hp.n_head,

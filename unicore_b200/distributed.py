@@ -1,10 +1,14 @@
-"""Multi-process (one rank per GPU) sharding of a proteome and the single exchange step of the path:
-an all-gather of the emitted 3Di byte strings before the DB write (north_star).
+"""Host arithmetic of the one-process-per-GPU path: count-sharding of a proteome and the placement of the gathered
+3Di bytes (north_star).  numpy only - no torch, no communication.
 
-Sequences are independent, so ranks share nothing during prediction.  The shard of every rank is a
-pure function of the sequence lengths, hence every rank knows every other rank's byte count and no
-length table has to be exchanged: one padded-slab all-gather (NCCL over NVLink on GPUs, gloo in the
-CPU tests) is the whole communication.
+The product's exchange step is in the library: `p5_predict_sharded` / `p5_allgather_3di` (csrc/comm.cc: one
+ncclAllGather of padded slabs, NCCL bound by the library itself) and `unicore-b200 createdb --procs N`.  The
+functions here are the Python mirror of csrc/comm.cc::shard_indices that bench.py uses to stage each rank's shard
+and that the CPU tests (tests/test_distributed.py: gloo, world size 2) check against the native one.
+
+Sequences are independent, so ranks share nothing during prediction.  The shard of every rank is a pure function
+of the sequence lengths, hence every rank knows every other rank's byte count and no length table has to be
+exchanged: one padded-slab all-gather is the whole communication.
 """
 from __future__ import annotations
 
@@ -50,24 +54,3 @@ def scatter_shards(rows, lengths: np.ndarray, offsets: np.ndarray) -> np.ndarray
             out[int(offsets[i]):int(offsets[i]) + n] = row[pos:pos + n]
             pos += n
     return out
-
-
-def allgather_3di(local: np.ndarray, lengths: np.ndarray, offsets: np.ndarray, device=None) -> np.ndarray:
-    """Every rank passes the letters of its shard (packed in shard order); returns the letters of ALL
-    sequences at `offsets` (input order).  Uses the default torch.distributed process group."""
-    import torch
-    import torch.distributed as dist
-
-    world, rank = dist.get_world_size(), dist.get_rank()
-    sizes = shard_sizes(lengths, world)
-    assert len(local) == sizes[rank], (len(local), sizes[rank])
-    slab = max(max(sizes), 1)
-    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
-                                             if dist.get_backend() == "nccl" else torch.device("cpu"))
-    send = torch.zeros(slab, dtype=torch.uint8, device=dev)
-    if len(local):
-        send[:len(local)].copy_(torch.from_numpy(np.ascontiguousarray(local)), non_blocking=False)
-    recv = torch.empty(world * slab, dtype=torch.uint8, device=dev)
-    dist.all_gather_into_tensor(recv, send)
-    recv = recv.cpu().numpy().reshape(world, slab)
-    return scatter_shards(recv, lengths, offsets)

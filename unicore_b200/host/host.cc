@@ -1,10 +1,13 @@
 #include "host.h"
 
 #include <dirent.h>
+#include <signal.h>
 #include <sys/stat.h>
+#include <sys/wait.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <chrono>
 #include <cstdio>
@@ -13,6 +16,7 @@
 #include <fstream>
 #include <map>
 #include <set>
+#include <thread>
 #include <unordered_map>
 
 #include "md5.h"
@@ -588,12 +592,168 @@ std::string read_checkpoint(const std::string& path) {
     return std::string((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
 }
 
+// One process per GPU (`--procs N`): the caller has done all the file work; here the process forks N-1 children BEFORE
+// any CUDA call (the records are inherited through fork, nothing is parsed twice), stays rank 0 itself, hands the
+// NCCL id to the children through pipes, and every rank predicts its count-shard; ONE ncclAllGather inside
+// p5_predict_sharded leaves all 3Di strings on every rank.  Rank 0 returns them to the caller (the only DB writer),
+// the children exit.  The communicator is set up on a thread of its own while the weights load.
+namespace {
+struct ChildWatch {  // a rank that dies would leave the others waiting inside NCCL for ever
+    std::vector<pid_t> pids;
+    std::atomic<bool> done{false};
+    std::thread th;
+    void start() {
+        th = std::thread([this] {
+            size_t alive = pids.size();
+            while (alive > 0) {
+                for (pid_t& pid : pids) {
+                    if (pid <= 0) continue;
+                    int st = 0;
+                    const pid_t r = waitpid(pid, &st, WNOHANG);
+                    if (r == pid) {
+                        pid = 0;
+                        --alive;
+                        if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0)) {
+                            fprintf(stderr, "Error: a prediction rank failed (%s %d)\n", WIFEXITED(st) ? "exit code" : "signal",
+                                    WIFEXITED(st) ? WEXITSTATUS(st) : WTERMSIG(st));
+                            for (pid_t q : pids)
+                                if (q > 0) kill(q, SIGTERM);
+                            _exit(ERR_GENERAL);
+                        }
+                    }
+                }
+                if (alive) usleep(done.load() ? 2000 : 50000);
+            }
+        });
+    }
+    void join() {
+        done = true;
+        if (th.joinable()) th.join();
+    }
+};
+}  // namespace
+
 std::vector<std::string> predict_3di(const std::string& model_dir, const std::vector<Record>& recs,
                                      const PredictOptions& opt) {
     using clk = std::chrono::steady_clock;
     std::vector<int> devs = opt.devices;
-    p5_model* m = nullptr;
+    const int world = opt.procs > 1 ? opt.procs : 1;
+    int rank = 0;
+    std::vector<int> id_pipes;  // rank 0: write ends towards ranks 1..N-1
+    int my_pipe = -1;
+    ChildWatch watch;
+    if (world > 1) {
+        if (devs.empty())
+            for (int r = 0; r < world; ++r) devs.push_back(r);
+        if (int(devs.size()) != world) die(ERR_ARGPARSE, "--procs N needs exactly N devices in --devices");
+        fflush(stdout);
+        fflush(stderr);
+        for (int r = 1; r < world; ++r) {
+            int fd[2];
+            if (pipe(fd) != 0) die(ERR_GENERAL, "pipe failed");
+            const pid_t pid = fork();
+            if (pid < 0) die(ERR_GENERAL, "fork failed");
+            if (pid == 0) {  // rank r
+                close(fd[1]);
+                for (int w : id_pipes) close(w);
+                rank = r;
+                my_pipe = fd[0];
+                id_pipes.clear();
+                watch.pids.clear();
+                break;
+            }
+            close(fd[0]);
+            id_pipes.push_back(fd[1]);
+            watch.pids.push_back(pid);
+        }
+        if (rank == 0) watch.start();
+    }
+    auto fail = [&](const std::string& what) {
+        if (rank == 0) die(ERR_GENERAL, what);
+        fprintf(stderr, "Error (rank %d): %s\n", rank, what.c_str());
+        _exit(ERR_GENERAL);
+    };
+
     const auto t0 = clk::now();
+    p5_comm* comm = nullptr;
+    std::thread comm_thread;
+    std::string comm_err;
+    double comm_s = 0;
+    if (world > 1) {
+        uint8_t id[P5_COMM_ID_BYTES];
+        if (rank == 0) {
+            if (p5_comm_unique_id(id) != 0) fail(std::string("NCCL: ") + p5_last_error());
+            for (int w : id_pipes) {
+                if (write(w, id, sizeof id) != ssize_t(sizeof id)) fail("could not hand the NCCL id to a rank");
+                close(w);
+            }
+        } else {
+            size_t got = 0;
+            while (got < sizeof id) {
+                const ssize_t n = read(my_pipe, id + got, sizeof id - got);
+                if (n <= 0) fail("could not read the NCCL id from rank 0");
+                got += size_t(n);
+            }
+            close(my_pipe);
+        }
+        const int dev = devs[rank];
+        comm_thread = std::thread([&, dev] {  // ~0.4 s of NCCL set-up, hidden behind the weight load
+            const auto c0 = clk::now();
+            uint8_t idc[P5_COMM_ID_BYTES];
+            memcpy(idc, id, sizeof idc);
+            if (p5_comm_create(idc, rank, world, dev, &comm) != 0) comm_err = p5_last_error();
+            comm_s = std::chrono::duration<double>(clk::now() - c0).count();
+        });
+        // the thread copies `id` first thing; keep it alive until the join below
+        p5_model* m = nullptr;
+        const int one = dev;
+        const int rc = p5_model_load(model_dir.c_str(), &one, 1, &m);
+        const std::string load_err = rc != 0 ? p5_last_error() : "";
+        comm_thread.join();
+        if (rc != 0) fail("ProstT5 model: " + load_err);
+        if (!comm_err.empty()) fail("NCCL communicator: " + comm_err);
+        const auto t1 = clk::now();
+        if (opt.max_batch_tokens > 0 && p5_set_option(m, "max_batch_tokens", opt.max_batch_tokens) != 0) fail(p5_last_error());
+        std::vector<uint64_t> off(recs.size() + 1, 0);
+        for (size_t i = 0; i < recs.size(); ++i) off[i + 1] = off[i] + recs[i].seq.size();
+        std::string aa;
+        aa.reserve(off.back());
+        for (const Record& r : recs) aa += r.seq;
+        std::string out(aa.size(), '\0');
+        if (p5_predict_sharded(m, comm, reinterpret_cast<const uint8_t*>(aa.data()), off.data(), recs.size(),
+                               reinterpret_cast<uint8_t*>(&out[0]), opt.split_len) != 0)
+            fail(std::string("ProstT5 prediction failed: ") + p5_last_error());
+        const auto t2 = clk::now();
+        double st[14] = {0};
+        p5_get_stats(m, st, 14);
+        p5_model_free(m);
+        p5_comm_free(comm);
+        if (rank != 0) {
+            fflush(stdout);
+            fflush(stderr);
+            _exit(0);
+        }
+        watch.join();
+        std::vector<std::string> ss(recs.size());
+        for (size_t i = 0; i < recs.size(); ++i) ss[i] = out.substr(off[i], off[i + 1] - off[i]);
+        const double load_s = std::chrono::duration<double>(t1 - t0).count();
+        const double pred_s = std::chrono::duration<double>(t2 - t1).count();
+        msg(3, "ProstT5: " + std::to_string(recs.size()) + " sequences, " + std::to_string(off.back()) + " residues on " +
+                   std::to_string(world) + " ranks in " + std::to_string(pred_s) + " s (" +
+                   std::to_string(off.back() / std::max(pred_s, 1e-9)) + " residues/s incl. the NCCL all-gather; weights + communicator in " +
+                   std::to_string(load_s) + " s, communicator alone " + std::to_string(comm_s) + " s)");
+        if (!opt.stats_json.empty()) {
+            std::ofstream js(opt.stats_json);
+            js << "{\"sequences\": " << recs.size() << ", \"residues\": " << off.back() << ", \"ranks\": " << world
+               << ", \"predict_seconds\": " << pred_s << ", \"load_seconds\": " << load_s << ", \"comm_init_seconds\": " << comm_s
+               << ", \"residues_per_second\": " << off.back() / std::max(pred_s, 1e-9) << ", \"rank0_batches\": " << st[0]
+               << ", \"rank0_tokens\": " << st[1] << ", \"rank0_kernel_launches\": " << st[3] << ", \"rank0_device_ms\": " << st[4]
+               << "}\n";
+        }
+        return ss;
+    }
+
+    p5_model* m = nullptr;
     if (p5_model_load(model_dir.c_str(), devs.empty() ? nullptr : devs.data(), devs.empty() ? -1 : int(devs.size()), &m) != 0)
         die(ERR_GENERAL, std::string("ProstT5 model: ") + p5_last_error());
     const auto t1 = clk::now();

@@ -100,6 +100,7 @@ std::vector<std::string> list_files_with_ext(const std::string& dir, const std::
 // runs the predictor over the records: returns one 3Di string per record (calls the C ABI)
 struct PredictOptions {
     std::vector<int> devices;  // empty = every visible device
+    int procs = 0;             // > 1: one process per GPU (fork), count-sharding + one NCCL all-gather
     uint32_t split_len = 0;
     int64_t max_batch_tokens = 0;  // 0 = library default
     std::string stats_json;        // optional path

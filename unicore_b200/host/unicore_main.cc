@@ -28,6 +28,8 @@ static const char* kUsage =
     "      --threads <THREADS>       Accepted for compatibility [default: 0]\n"
     "  -v, --verbosity <VERBOSITY>   0: quiet, 1: +errors, 2: +warnings, 3: +info, 4: +debug [default: 3]\n"
     "      --devices <LIST>          Comma-separated CUDA devices (default: all visible)\n"
+    "      --procs <N>               One process per GPU on N GPUs: sequences sharded by count, one NCCL all-gather of\n"
+    "                                the 3Di strings, this process writes the DB (default: threads in one process)\n"
     "      --split-len <N>           Predict sequences longer than N residues in chunks of N (default 0: never)\n"
     "      --max-batch-tokens <N>    Tokens per forward pass\n"
     "      --stats-json <PATH>       Write throughput counters as JSON\n";
@@ -61,7 +63,8 @@ static int createdb(int argc, char** argv) {
                 if (e > s) popt.devices.push_back(atoi(v.substr(s, e - s).c_str()));
                 s = e + 1;
             }
-        } else if (a == "--split-len") popt.split_len = uint32_t(atol(value("split_len").c_str()));
+        } else if (a == "--procs") popt.procs = atoi(value("procs").c_str());
+        else if (a == "--split-len") popt.split_len = uint32_t(atol(value("split_len").c_str()));
         else if (a == "--max-batch-tokens") popt.max_batch_tokens = atol(value("max_batch_tokens").c_str());
         else if (a == "--stats-json") popt.stats_json = value("stats_json");
         else if (a == "-h" || a == "--help") { fputs(kUsage, stdout); return 0; }

@@ -30,6 +30,59 @@ def pack_sequences(seqs: Iterable[bytes]):
     return aa, offsets
 
 
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """The 128-byte NCCL id rank 0 creates and hands to the other ranks by any side channel."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    _lib.check(_lib.load().p5_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def shard_indices_native(offsets: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """The library's own count-sharding (csrc/comm.cc) - host arithmetic only, no GPU needed."""
+    offsets = np.ascontiguousarray(offsets, np.uint64)
+    n = len(offsets) - 1
+    idx = np.zeros(max(n, 1), np.uint64)
+    cnt = C.c_uint64(0)
+    _lib.check(_lib.load().p5_shard_indices(offsets.ctypes.data, n, rank, world, idx.ctypes.data, C.byref(cnt)))
+    return idx[:cnt.value].astype(np.int64)
+
+
+class Comm:
+    """One rank of the library's NCCL communicator (one process per GPU); see include/prostt5_b200.h."""
+
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: int):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        assert len(unique_id) == COMM_ID_BYTES
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        _lib.check(self._lib.p5_comm_create(buf, rank, world, device, C.byref(self._h)))
+        r, w, v = C.c_int(0), C.c_int(0), C.c_int(0)
+        _lib.check(self._lib.p5_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
+        self.rank, self.world, self.nccl_version = r.value, w.value, v.value
+
+    def allgather_3di(self, local: np.ndarray, offsets: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        local = np.ascontiguousarray(local, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        if out is None:
+            out = np.zeros(int(offsets[-1]), np.uint8)
+        _lib.check(self._lib.p5_allgather_3di(self._h, local.ctypes.data, offsets.ctypes.data, len(offsets) - 1, out.ctypes.data))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.p5_comm_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Predictor:
     def __init__(self, model_dir: str, devices: Sequence[int] | None = None):
         self._lib = _lib.load()
@@ -85,6 +138,17 @@ class Predictor:
             out = np.zeros(len(aa), np.uint8)
         _lib.check(self._lib.p5_predict(self._h, aa.ctypes.data, offsets.ctypes.data, len(offsets) - 1, out.ctypes.data,
                                         split_len))
+        return out
+
+    def predict_sharded(self, comm: "Comm | None", aa: np.ndarray, offsets: np.ndarray, split_len: int = 0,
+                        out: np.ndarray | None = None):
+        """Every rank passes the WHOLE proteome; the library predicts this rank's count-shard and all-gathers the 3Di
+        bytes over NCCL: `out` holds the letters of all sequences on every rank."""
+        self._check_packed(aa, offsets)
+        if out is None:
+            out = np.zeros(len(aa), np.uint8)
+        _lib.check(self._lib.p5_predict_sharded(self._h, comm._h if comm is not None else None, aa.ctypes.data,
+                                                offsets.ctypes.data, len(offsets) - 1, out.ctypes.data, split_len))
         return out
 
     def predict(self, seqs: Iterable[bytes], split_len: int = 0) -> list[bytes]:
