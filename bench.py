@@ -225,7 +225,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-4 / config-5 steps")
     ap.add_argument("--cpu-sample-seqs", type=int, default=6)
-    ap.add_argument("--attn-impl", type=int, default=-1, help="A/B: library option attn_impl (default: the library's)")
+    ap.add_argument("--attn-impl", type=int, default=-1,
+                    help="A/B only: run on libprostt5_b200_debug.so with its option attn_impl (0, 2, 3); never used by the driver")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -282,7 +283,7 @@ def main():
     aa, off = D.take_shard(aa_all, off_all, idx)
     total_res = int(off_all[-1])
 
-    pred = Predictor(MODEL_DIR, devices=[local_rank])
+    pred = Predictor(MODEL_DIR, devices=[local_rank], debug=args.attn_impl >= 0)
     pred.set_option("profile", 1)
     if args.attn_impl >= 0:
         pred.set_option("attn_impl", args.attn_impl)

@@ -68,8 +68,12 @@ int p5_bias_table(const p5_model* m, uint32_t head, float* out);
  *   "head_include_eos"  1 (default): the </s> row is part of the CNN head's input, as in the Rostlab
  *                       ProstT5 script applied to a batch of one; 0: zero padding starts right after the
  *                       last residue
+ *   "map_rare_to_x"     1 (default): U, Z, O, B tokenise as X, as ProstT5's published preprocessing does; 0: they take
+ *                       their own vocabulary tokens (what a plain vocabulary lookup would do; which of the two Foldseek
+ *                       does is unverified here, tools/compare_with_foldseek.sh reports both)
  *   "gemm_variant"      1 (default) CTA-pair tcgen05 GEMM, 0 single-CTA
- *   "attn_impl"         1 (default) tcgen05 attention kernel, 0 legacy mma.sync kernel
+ *   "attn_impl"         1: the tcgen05 attention kernel (the only one in this library; the A/B implementations
+ *                       0 = mma.sync, 2, 3 exist in libprostt5_b200_debug.so)
  *   "profile"           1: time every kernel class with CUDA events on the launch stream (p5_get_stats) */
 int p5_set_option(p5_model* m, const char* key, int64_t value);
 

@@ -12,6 +12,8 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with `-m gpu` on the GPU box)")
     # built artefacts are git-ignored: build them once if a fresh checkout has none (nvcc cross-compiles without a GPU)
     need = [os.path.join(ROOT, "unicore_b200", "lib", "libprostt5_b200.so"),
+            os.path.join(ROOT, "unicore_b200", "lib", "libprostt5_b200_debug.so"),
+            os.path.join(ROOT, "oracle", "lib", "libprostt5_oracle.so"),
             os.path.join(ROOT, "unicore_b200", "lib", "libunicore_host.so"),
             os.path.join(ROOT, "unicore_b200", "bin", "unicore-b200"),
             os.path.join(ROOT, "unicore_b200", "bin", "foldseek-b200")]

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""Generates tests/golden/example_data_host.json from /root/reference/example/data with the host oracle
-(oracle/host_oracle.py): per-file record counts, totals, and an md5 over the sorted .map lines.  The
-example FASTA files themselves are reference content and are NOT copied; the CPU test that consumes
-this fixture re-reads them only when /root/reference exists (it does not on the GPU box)."""
+"""Generates tests/golden/example_data_host.json from the reference's example/data (copied as a fixture to
+tests/golden/example_data) with the host oracle (oracle/host_oracle.py): record counts, totals, and an md5
+over the sorted .map lines.  NOTE: this is "two restatements agree" (the Python restatement of the reference's
+Rust here, the C++ host in the tests), not output of the compiled Rust: there is no Rust toolchain in this image."""
 import hashlib
 import json
 import os
@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle import host_oracle as H  # noqa: E402
 
-SRC = "/root/reference/example/data"
+SRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "example_data")
 data, lines = H.collect(SRC)
 out = {
     "files": len(H.list_inputs(SRC)),

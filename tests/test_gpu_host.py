@@ -151,3 +151,51 @@ def test_createdb_procs_two_ranks(tmp_path, tiny_dir, tiny_oracle):
     for suffix in ("", ".index", ".dbtype", "_ss", "_ss.index", "_ss.dbtype", "_h", "_h.index", "_h.dbtype", ".lookup"):
         assert open(outs[0] + suffix, "rb").read() == open(outs[1] + suffix, "rb").read(), suffix
     _check_ss(H.check_foldseek_db(outs[1]), tiny_oracle)
+
+
+def test_example_data_createdb_on_the_gpu(tmp_path, full_dir):
+    """BASELINE config 3: the reference's example/data (30 files, 1,276 records, 393,397 residues, 23 records longer
+    than 1,024 aa) through `unicore-b200 createdb` with the full-size model on the B200, then the conformance checker
+    that restates what the reference's own consumers do with the DB (`read_db` zipping <db>_h / <db> / <db>_ss by line
+    [REF src/seq/create_gene_specific_fasta.rs:9-44]; .index / .dbtype / .lookup as `foldseek cluster` re-opens them
+    [REF src/modules/cluster.rs:45-72]) and the .map contract of `profile` [REF src/modules/profile.rs:18-27]."""
+    import hashlib
+    import json
+    src = os.path.join(os.path.dirname(__file__), "golden", "example_data")
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "example_data_host.json")))
+    out = tmp_path / "o" / "proteome_db"
+    stats = tmp_path / "stats.json"
+    p = subprocess.run([UNICORE, "createdb", src, str(out), full_dir, "--devices", "0", "--stats-json", str(stats)],
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "23 sequences are longer than 1024 residues" in p.stdout  # default = Foldseek's believed split length
+    entries = H.check_foldseek_db(str(out))
+    assert len(entries) == gold["unique_records"] == 1276
+    assert sum(len(a) for _, a, _ in entries) == gold["residues"] == 393397
+    for name, aa, ss in entries:
+        assert name == H.hashed_name(aa) and len(ss) == len(aa) and set(ss) <= set("ACDEFGHIKLMNPQRSTVWY")
+    assert sum(len(a) > 1024 for _, a, _ in entries) == 23
+    lines = sorted(open(str(out) + ".map").read().splitlines(keepends=True))
+    assert hashlib.md5("".join(lines).encode()).hexdigest() == gold["map_sorted_md5"]
+    assert (out.parent / "createdb.chk").read_text() == "1" and not (out.parent / "combined_aa.fasta").exists()
+    st = json.load(open(stats))
+    print(f"config 3 on the B200: {st['sequences']} sequences, {st['residues']} residues, "
+          f"{st['residues_per_second']:.0f} residues/s end to end (predict {st['predict_seconds']:.2f} s, load {st['load_seconds']:.2f} s)")
+    # the tree-side consumer of the reference accepts the DB [REF src/modules/tree.rs:69]: per-gene FASTA of two "genes"
+    prof = tmp_path / "profile"
+    prof.mkdir()
+    (prof / "gene1.txt").write_text("".join(f"{n}\tSp{k}\n" for k, (n, _, _) in enumerate(entries[:5])))
+    p = subprocess.run([UNICORE, "genefasta", str(out), str(prof), str(tmp_path / "tree")], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    # same records predicted in one piece (--split-len 0): only the 23 long records may change
+    out2 = tmp_path / "o2" / "proteome_db"
+    p = subprocess.run([UNICORE, "createdb", src, str(out2), full_dir, "--devices", "0", "--split-len", "0", "-v", "0"],
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout + p.stderr
+    a = {n: ss for n, _, ss in entries}
+    b = {n: (aa, ss) for n, aa, ss in H.check_foldseek_db(str(out2))}
+    assert set(a) == set(b)
+    changed = [n for n in a if a[n] != b[n][1]]
+    assert all(len(b[n][0]) > 1024 for n in changed)
+    print(f"split length 1024 (default) vs 0 changes {len(changed)} of the 23 records longer than 1,024 aa "
+          "(Q2: the reference passes no split flag, Foldseek's own default applies)")

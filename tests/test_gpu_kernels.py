@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _gemm(variant, epi, M, N, K, seed):
-    lib = _lib.load()
+    lib = _lib.load_debug()
     rng = np.random.default_rng(seed)
     a = (rng.standard_normal((M, K), dtype=np.float32) * 0.5).astype(np.float16)
     b = (rng.standard_normal((N, K), dtype=np.float32) * 0.5).astype(np.float16)
@@ -51,7 +51,7 @@ def test_gemm_matches_numpy(variant, epi, M, N, K):
 
 
 def test_gemm_gated_epilogue():
-    lib = _lib.load()
+    lib = _lib.load_debug()
     rng = np.random.default_rng(9)
     M, N, K = 300, 512, 256  # N = 2 * d_ff: gate/up rows interleaved
     a = (rng.standard_normal((M, K), dtype=np.float32) * 0.5).astype(np.float16)
@@ -103,7 +103,7 @@ def _attention_ref(qkv, cu, H, bias, md):
                                     ([700, 66, 1026], 2), ([2500], 1), ([128, 129, 127, 256, 257], 3),
                                     ([16, 17, 33, 48, 49, 80, 81, 96, 97, 112, 113, 4002], 2)])
 def test_attention_matches_numpy(lens, H, impl):
-    lib = _lib.load()
+    lib = _lib.load_debug()
     rng = np.random.default_rng(sum(lens) + H)
     cu = np.zeros(len(lens) + 1, np.int32)
     cu[1:] = np.cumsum(lens)
@@ -131,7 +131,7 @@ def _many_lens(seed, n, lo, hi):
 @pytest.mark.parametrize("lens,H", [(_many_lens(1, 90, 3, 420), 5), (_many_lens(2, 400, 3, 70), 3),
                                     ([352] * 40, 8), (_many_lens(3, 12, 900, 1500), 4)])
 def test_attention_many_items(lens, H, impl):
-    lib = _lib.load()
+    lib = _lib.load_debug()
     rng = np.random.default_rng(len(lens) + H)
     cu = np.zeros(len(lens) + 1, np.int32)
     cu[1:] = np.cumsum(lens)
@@ -148,7 +148,7 @@ def test_attention_many_items(lens, H, impl):
 
 def test_attention_feature_variants_bit_identical():
     """The pipelining features only reorder independent work: same bits out for every mask."""
-    lib = _lib.load()
+    lib = _lib.load_debug()
     lens, H, md = _many_lens(5, 120, 3, 500), 4, 128
     rng = np.random.default_rng(11)
     cu = np.zeros(len(lens) + 1, np.int32)
@@ -167,10 +167,38 @@ def test_attention_feature_variants_bit_identical():
         np.testing.assert_array_equal(o.view(np.uint16), outs[0].view(np.uint16))
 
 
+def test_attention_table_ring_wraps_bit_identical():
+    """The bias table of the product kernel is fetched by the TMA producer (cp.async.bulk into a two-slot full/empty
+    mbarrier ring, one head ahead); compute-sanitizer's racecheck does not model the complete_tx / try_wait pair that
+    orders it against the softmax warps' ld.shared and reports a hazard (profiles/r01/racecheck_pass2_mask15.txt).
+    This is the targeted check: fewer work items per head (100) than resident CTAs (296), 8 heads -> every CTA changes
+    head at EVERY item and goes through 3+ table loads, so the ring wraps and each slot is refilled while neighbours
+    still read the other one; the result must be bit-identical to the variant whose softmax warps load the table
+    themselves behind a named barrier (mask 14, racecheck-clean), run after run, and match numpy."""
+    lib = _lib.load_debug()
+    lens, H, md = _many_lens(7, 100, 20, 129), 8, 128
+    rng = np.random.default_rng(23)
+    cu = np.zeros(len(lens) + 1, np.int32)
+    cu[1:] = np.cumsum(lens)
+    M = int(cu[-1])
+    qkv = (rng.standard_normal((M, 3 * H * 128), dtype=np.float32) * 0.8).astype(np.float16)
+    bias = (rng.standard_normal((H, 2 * md + 1), dtype=np.float32) * 2.0).astype(np.float32)  # tables that differ a lot
+    outs = []
+    for impl in (16 + 14, 16 + 15, 1, 16 + 15, 16 + 14):
+        ctx = np.zeros((M, H * 128), np.float16)
+        ms = C.c_float(0)
+        _lib.check(lib.p5_dbg_attention(0, impl, qkv.ctypes.data, cu.ctypes.data, len(lens), H, md, bias.ctypes.data,
+                                        ctx.ctypes.data, 5, C.byref(ms)))  # + 5 timed repeats over the same buffers
+        outs.append(ctx)
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o.view(np.uint16), outs[0].view(np.uint16))
+    assert np.abs(outs[0].astype(np.float32) - _attention_ref(qkv, cu, H, bias, md)).max() < 6e-3
+
+
 @pytest.mark.parametrize("impl", _impls([3, 2, 1, 0]))
 def test_attention_peaked_scores(impl):
     """Un-scaled T5 scores can be large: one dominant key per row must not overflow or lose the row."""
-    lib = _lib.load()
+    lib = _lib.load_debug()
     rng = np.random.default_rng(3)
     T, H, md = 200, 1, 128
     cu = np.array([0, T], np.int32)
@@ -188,7 +216,7 @@ def test_attention_peaked_scores(impl):
 @pytest.mark.parametrize("impl", _impls([3, 2, 1, 16, 0]))
 def test_attention_peaked_scores_many_items(impl):
     """Accumulator rescales (large un-scaled scores) while items are pipelined back to back in each CTA."""
-    lib = _lib.load()
+    lib = _lib.load_debug()
     rng = np.random.default_rng(9)
     lens, H, md = _many_lens(9, 60, 150, 420), 6, 128
     cu = np.zeros(len(lens) + 1, np.int32)
@@ -210,7 +238,7 @@ def test_attention_is_independent_of_the_neighbour_sequence(impl):
     """Packed layout: the query rows past a sequence's end are the next sequence's tokens.  They must not leak into the
     sequence's own rows - not even through the warp-wide vote that triggers an accumulator rescale (peaked scores make
     those frequent).  Found on a 1-GPU vs 2-GPU createdb whose _ss files differed in a few residues."""
-    lib = _lib.load()
+    lib = _lib.load_debug()
     rng = np.random.default_rng(17)
     H, md = 2, 128
     bias = (rng.standard_normal((H, 2 * md + 1), dtype=np.float32) * 0.5).astype(np.float32)
@@ -232,7 +260,7 @@ def test_attention_is_independent_of_the_neighbour_sequence(impl):
 
 def test_gemm_fp16_outputs_saturate():
     """Values beyond the fp16 range are stored as +-65504, not inf (same policy as the oracle's _r16)."""
-    lib = _lib.load()
+    lib = _lib.load_debug()
     M, N, K = 128, 256, 64
     a = np.full((M, K), 200.0, np.float16)
     b = np.full((N, K), 100.0, np.float16)
@@ -255,7 +283,7 @@ def _rmsnorm_ref(x, w, eps):
 def test_rmsnorm_matches_numpy(M, d):
     """p3/p9: fp32 statistics, fp16 (saturating) operand out, optional fp32 copy; rows longer than 1024 take the
     re-read path of the kernel."""
-    lib = _lib.load()
+    lib = _lib.load_debug()
     rng = np.random.default_rng(M + d)
     h = (rng.standard_normal((M, d), dtype=np.float32) * rng.uniform(0.1, 300.0, (M, 1)).astype(np.float32))
     w = (1.0 + 0.1 * rng.standard_normal(d, dtype=np.float32)).astype(np.float32)
@@ -269,7 +297,7 @@ def test_rmsnorm_matches_numpy(M, d):
 
 
 def test_rmsnorm_saturates_to_fp16_range():
-    lib = _lib.load()
+    lib = _lib.load_debug()
     h = np.zeros((2, 128), np.float32)
     h[0, 0], h[1, :] = 1.0, 1.0
     w = np.full(128, 1e5, np.float32)  # |rmsnorm * w| far beyond 65504 in row 0
@@ -281,7 +309,7 @@ def test_rmsnorm_saturates_to_fp16_range():
 def test_embed_rmsnorm_matches_numpy():
     """p2 + p3 of layer 0: gather of the fp16 embedding rows into the fp32 residual stream, then the norm;
     ids outside the vocabulary read row 0 (defensive: the tokenizer LUT never emits them)."""
-    lib = _lib.load()
+    lib = _lib.load_debug()
     rng = np.random.default_rng(4)
     V, d, M = 150, 1024, 777
     embd = (rng.standard_normal((V, d), dtype=np.float32) * 0.7).astype(np.float16)
@@ -326,7 +354,7 @@ def _head_ref(taps, cu, b0, w1, b1, include_eos):
 def test_head_matches_numpy(include_eos):
     """p10 + p11: shifted tap sum with per-sequence zero padding (never a neighbour's rows), ReLU, second conv,
     20-way arg-max with ties to the lowest class; chunk boundaries at 64 residues."""
-    lib = _lib.load()
+    lib = _lib.load_debug()
     rng = np.random.default_rng(8)
     lens = [1, 2, 3, 63, 64, 65, 130, 300, 7]
     cu = np.zeros(len(lens) + 1, np.int32)
@@ -351,7 +379,7 @@ def test_head_matches_numpy(include_eos):
 
 
 def test_head_argmax_ties_go_to_the_lowest_class():
-    lib = _lib.load()
+    lib = _lib.load_debug()
     cu = np.array([0, 12], np.int32)  # one sequence of 10 residues
     c1, ncls, ks = 32, 20, 7
     taps = np.zeros((12, ks * c1), np.float32)

@@ -112,6 +112,15 @@ def test_non_standard_residues(tiny, tiny_oracle):
     _check_against_oracle(tiny, tiny_oracle, seq, TINY_HID_TOL, TINY_LOGIT_TOL)
     assert tiny.predict([b"MKUZOB"]) == tiny.predict([b"MKXXXX"])  # rare residues tokenise as X
     assert tiny.predict([b"mktayi"]) == tiny.predict([b"MKTAYI"])  # case-insensitive
+    # option map_rare_to_x = 0: U, Z, O, B take their own vocabulary tokens (a plain vocabulary lookup)
+    toks = spec.vocab_tokens()
+    tiny.set_option("map_rare_to_x", 0)
+    lut = tiny.token_table()
+    assert [toks[lut[ord(c)]] for c in "UZOBuzob"] == ["▁U", "▁Z", "▁O", "▁B"] * 2 and toks[lut[ord("J")]] == "▁X"
+    hid_own = tiny.encode_debug(b"MKUZOB")[0]
+    tiny.set_option("map_rare_to_x", 1)
+    np.testing.assert_array_equal(tiny.token_table(), tiny_oracle.lut)
+    assert np.abs(hid_own - tiny.encode_debug(b"MKUZOB")[0]).max() > 1e-3  # different embeddings went in
 
 
 def test_batching_invariance_and_order(tiny):
@@ -309,15 +318,23 @@ def test_full_size_ragged_batching_invariance(full):
         assert full.encode_debug(s)[2] == a[int(off[i]):int(off[i + 1])].tobytes()
 
 
-def test_attention_implementations_agree_at_full_size(full):
-    """The tcgen05 kernel and the independent mma.sync kernel differ only in rounding (fp16 P against different
-    running maxima): the letters they give must agree on nearly every residue of a ragged full-size batch."""
+def test_attention_implementations_agree_at_full_size(full, full_dir):
+    """The product's tcgen05 kernel against the independent implementations of the debug library (mma.sync, two softmax
+    warpgroups, packed-pair math): they differ only in rounding (fp16 P against different running maxima, summation
+    order of the row sums), so the letters must agree on nearly every residue of a ragged full-size batch; and the
+    debug build of the product kernel gives the product's bytes."""
     aa, off = spec.synthetic_proteome("config4", n=60)
     a = full.predict_packed(aa, off)
-    full.set_option("attn_impl", 0)
-    b = full.predict_packed(aa, off)
-    full.set_option("attn_impl", 1)
-    assert (a != b).mean() < 0.01
+    with Predictor(full_dir, debug=True) as dbg:
+        np.testing.assert_array_equal(dbg.predict_packed(aa, off), a)
+        for impl in (0, 2, 3):
+            dbg.set_option("attn_impl", impl)
+            b = dbg.predict_packed(aa, off)
+            print(f"attn_impl {impl}: {int((a != b).sum())} of {len(a)} letters differ from the product kernel's")
+            assert (a != b).mean() < 0.01
+    from unicore_b200._lib import P5Error
+    with pytest.raises(P5Error):
+        full.set_option("attn_impl", 0)  # the product library carries one attention kernel
 
 
 def test_in_process_multi_device(tiny_dir):

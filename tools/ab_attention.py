@@ -33,7 +33,7 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--out", default="")
     a = ap.parse_args()
-    lib = _lib.load()
+    lib = _lib.load_debug()
     rng = np.random.default_rng(0)
     # (token counts, scale of the random q/k/v): scale 0.6 gives small un-scaled scores (the lazy rescale of the
     # accumulator almost never fires), scale 3.0 gives |q.k| up to ~1000 as trained T5 weights can (rescales are timed)

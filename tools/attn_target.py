@@ -20,6 +20,6 @@ qkv = (rng.standard_normal((M, 3 * H * 128), dtype=np.float32) * 0.6).astype(np.
 bias = (rng.standard_normal((H, 257), dtype=np.float32) * 0.5).astype(np.float32)
 ctx = np.zeros((M, H * 128), np.float16)
 ms = C.c_float(0)
-_lib.check(_lib.load().p5_dbg_attention(0, impl, qkv.ctypes.data, cu.ctypes.data, len(lens), H, 128, bias.ctypes.data,
+_lib.check(_lib.load_debug().p5_dbg_attention(0, impl, qkv.ctypes.data, cu.ctypes.data, len(lens), H, 128, bias.ctypes.data,
                                         ctx.ctypes.data, 3, C.byref(ms)))
 print("impl", impl, shape, "%.3f ms" % ms.value)

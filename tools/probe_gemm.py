@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 def run_case(variant, epi, M, N, K):
     import ctypes as C
     from unicore_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_debug()
     rng = np.random.default_rng(M * 7 + N * 3 + K + epi)
     a = (rng.standard_normal((M, K), dtype=np.float32) * 0.5).astype(np.float16)
     b = (rng.standard_normal((N, K), dtype=np.float32) * 0.5).astype(np.float16)
@@ -58,7 +58,7 @@ def run_case(variant, epi, M, N, K):
 def run_bench(variant, epi, M, N, K, iters):
     import ctypes as C
     from unicore_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_debug()
     ms = C.c_float(0)
     rc = lib.p5_dbg_gemm_bench(0, variant, epi, M, N, K, iters, C.byref(ms))
     if rc != 0:

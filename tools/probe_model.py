@@ -39,7 +39,7 @@ def attn_ref(qkv, cu, H, bias, md):
 def stage_attn(impl=1):
     import ctypes as C
     from unicore_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_debug()
     res = []
     for lens, H in (([3], 1), ([64], 2), ([65, 1, 130], 2), ([352, 352], 4), ([700, 66, 1026], 2)):
         rng = np.random.default_rng(sum(lens) + H)

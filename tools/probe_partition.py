@@ -13,7 +13,7 @@ ap.add_argument("--iters", type=int, default=120)
 ap.add_argument("--sms", default="128,120,136")
 ap.add_argument("--out", default="")
 a = ap.parse_args()
-lib = _lib.load()
+lib = _lib.load_debug()
 res = []
 for sms in [int(x) for x in a.sms.split(",")]:
     out = (C.c_float * 8)()

@@ -19,7 +19,7 @@ with Predictor(d) as p:
 # TMA-store epilogue and its direct-store fallback for ragged tails)
 import ctypes as C
 from unicore_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_debug()
 lens = [int(x) for x in rng.integers(3, 300, 220)]
 H, md = 3, 128
 cu = np.zeros(len(lens) + 1, np.int32)

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 SHAPES = {"qkv": (0, 90112, 12288, 1024), "o": (2, 90112, 1024, 4096), "ffn_in": (1, 90112, 16384, 1024), "ffn_out": (2, 90112, 1024, 16384)}
 if len(sys.argv) > 1 and sys.argv[1] == "--one":
     from unicore_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_debug()
     v, name = int(sys.argv[2]), sys.argv[3]
     epi, M, N, K = SHAPES[name]
     ms = C.c_float(0)

@@ -10,7 +10,7 @@ sys.path.insert(0, ROOT)
 SHAPES = {"o": (2, 90112, 1024, 4096), "ffn_out": (2, 90112, 1024, 16384), "ffn_in": (1, 90112, 16384, 1024)}
 if len(sys.argv) > 1 and sys.argv[1] == "--one":
     from unicore_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_debug()
     epi, M, N, K = SHAPES[sys.argv[2]]
     ms = C.c_float(0)
     iters = int(os.environ.get("SWEEP_ITERS", "2"))

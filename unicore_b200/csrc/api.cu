@@ -8,7 +8,16 @@
 #include "model.h"
 #include "prostt5_b200.h"
 
+namespace p5 {
+namespace {
+thread_local std::string g_last_error;
+}
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace p5
+
 using namespace p5;
+
+extern "C" const char* p5_last_error(void) { return p5::g_last_error.c_str(); }
 
 struct p5_model {
     Model* m;
@@ -81,9 +90,17 @@ extern "C" int p5_set_option(p5_model* h, const char* key, int64_t value) {
                 model_rebuild_weight_maps(*h->m);
             }
         } else if (k == "attn_impl") {
+#ifdef P5_DEBUG_BUILD
             P5_REQUIRE(value >= 0 && value <= 3, P5_ERR_ARG,
-                       "attn_impl must be 0 (mma.sync), 1 (tcgen05, first kernel), 2 (tcgen05, two softmax warpgroups) or 3 (tcgen05, packed-pair math)");
+                       "attn_impl must be 0 (mma.sync), 1 (tcgen05, the product kernel), 2 (tcgen05, two softmax warpgroups) or 3 (tcgen05, packed-pair math)");
+#else
+            P5_REQUIRE(value == 1, P5_ERR_ARG, "attn_impl: this library carries the tcgen05 kernel (1) only; the A/B "
+                                               "implementations 0, 2, 3 are in libprostt5_b200_debug.so");
+#endif
             o.attn_impl = int(value);
+        } else if (k == "map_rare_to_x") {
+            o.map_rare_to_x = value != 0;
+            model_rebuild_token_table(*h->m);
         } else if (k == "profile") {
             o.profile = value != 0;
         } else {

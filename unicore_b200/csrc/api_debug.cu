@@ -15,13 +15,6 @@
 
 namespace p5 {
 
-namespace {
-thread_local std::string g_last_error;
-}
-
-void set_last_error(const std::string& msg) { g_last_error = msg; }
-const char* last_error_cstr() { return g_last_error.c_str(); }
-
 struct ScratchBuf {
     void* p = nullptr;
     explicit ScratchBuf(size_t bytes) { P5_CUDA(cudaMalloc(&p, bytes ? bytes : 1)); }
@@ -298,4 +291,4 @@ extern "C" int p5_dbg_head(int device, const float* taps_host, const int32_t* cu
     });
 }
 
-extern "C" const char* p5_last_error(void) { return p5::last_error_cstr(); }
+

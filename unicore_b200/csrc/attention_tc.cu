@@ -481,7 +481,9 @@ namespace {
 using AttnKernel = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, __half*, const int4*, uint32_t, uint32_t, uint32_t,
                             const float*);
 AttnKernel attn_kernel(uint32_t feat) {
-    switch (feat) {  // the instantiated feature masks
+    switch (feat) {  // the instantiated feature masks: the product library carries the default only
+        case 15: return attention_tc_kernel<15>;
+#ifdef P5_DEBUG_BUILD
         case 0: return attention_tc_kernel<0>;
         case 1: return attention_tc_kernel<1>;
         case 2: return attention_tc_kernel<2>;
@@ -489,14 +491,18 @@ AttnKernel attn_kernel(uint32_t feat) {
         case 7: return attention_tc_kernel<7>;
         case 8: return attention_tc_kernel<8>;
         case 14: return attention_tc_kernel<14>;
-        case 15: return attention_tc_kernel<15>;
+#endif
         default: throw Error(P5_ERR_ARG, strf("attention feature mask %u is not built", feat));
     }
 }
 }  // namespace
 
 void attention_tc_init_device() {
+#ifdef P5_DEBUG_BUILD
     for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u})
+#else
+    for (uint32_t f : {15u})
+#endif
         P5_CUDA(cudaFuncSetAttribute(attn_kernel(f), cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemDynamic)));
 }
 
@@ -512,7 +518,7 @@ void attention_tc_build_table(const float* bias, uint32_t H, uint32_t max_dist, 
 }
 
 int attention_tc_default_features() {
-    static const int f = getenv("P5_ATTN_FEAT") ? atoi(getenv("P5_ATTN_FEAT")) : 15;  // experiment knob
+    static const int f = env_knob("P5_ATTN_FEAT", 15);  // experiment knob (debug library only)
     return f;
 }
 
@@ -525,7 +531,7 @@ void launch_attention_tc(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, 
     P5_REQUIRE((reinterpret_cast<uintptr_t>(e_ext) & 15) == 0, P5_ERR_ARG, "attention bias table is not 16-byte aligned");
     const uint64_t n_items = uint64_t(n_work) * H;
     P5_REQUIRE(n_items < (1ull << 31), P5_ERR_UNSUPPORTED, "too many attention work items");
-    static const int ctas_per_sm = getenv("P5_ATTN_CTAS") ? atoi(getenv("P5_ATTN_CTAS")) : 2;  // experiment knob
+    static const int ctas_per_sm = env_knob("P5_ATTN_CTAS", 2);  // experiment knob (debug library only)
     const uint32_t grid = uint32_t(std::min<uint64_t>(n_items, uint64_t(ctas_per_sm * num_sms)));
     const uint32_t feat = uint32_t(features < 0 ? attention_tc_default_features() : features);
     attn_kernel(feat)<<<grid, kThreads, kSmemDynamic, st>>>(tm_q, tm_kv, tm_ctx, ctx, work128, n_work, uint32_t(n_items), H, e_ext);

@@ -49,7 +49,6 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays below 2^8 between rescales
 constexpr float kHeadRoom = 6.0f;          // log2 units added to the first tile's row max: P starts at <= 2^-6 and
                                            // rescales of the accumulator become rare
-constexpr uint32_t kNegInf = 0xff800000u;
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
@@ -319,41 +318,54 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     const bool bias_const = dmax <= -128 || dmin >= 128;
                     const float e_c = dmax <= -128 ? e_lo : e_hi;
                     const uint32_t er = es_row + uint32_t(j0) * 4;
-                    uint32_t v0[32], v1[32];
-                    ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN, v0);
-                    if (nv > 32) ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN + 32, v1);
-                    ptx::tmem_ld_wait();
-                    float2 z[32];  // z[p] = scores 2p, 2p+1 in the log2 domain
+                    const bool full = nv == int(kBN);  // every tile but an item's last one: straight-line code
+                    float2 z[32];                      // z[p] = scores 2p, 2p+1 in the log2 domain
                     const float2 l2e = make_float2(kLog2e, kLog2e);
+                    if (full) {
+                        uint32_t v0[32], v1[32];
+                        ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN, v0);
+                        ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN + 32, v1);
+                        ptx::tmem_ld_wait();
+                        if (bias_const) {  // (warp-uniform: the table is not even addressable for far tiles)
+                            const float2 e2 = make_float2(e_c, e_c);
 #pragma unroll
-                    for (int grp = 0; grp < 4; ++grp) {  // 16-column groups: whole, cut by the sequence end, or absent
-                        if (grp * 16 < nv) {
-                            if (bias_const) {  // (warp-uniform: the table is not even addressable for far tiles)
-                                const float2 e2 = make_float2(e_c, e_c);
-#pragma unroll
-                                for (int p = grp * 8; p < grp * 8 + 8; ++p) {
-                                    const float2 s = p < 16 ? make_float2(__uint_as_float(v0[2 * p]), __uint_as_float(v0[2 * p + 1]))
-                                                            : make_float2(__uint_as_float(v1[2 * p - 32]), __uint_as_float(v1[2 * p - 31]));
-                                    z[p] = __ffma2_rn(s, l2e, e2);
-                                }
-                            } else {
-#pragma unroll
-                                for (int p = grp * 8; p < grp * 8 + 8; ++p) {
-                                    const float2 s = p < 16 ? make_float2(__uint_as_float(v0[2 * p]), __uint_as_float(v0[2 * p + 1]))
-                                                            : make_float2(__uint_as_float(v1[2 * p - 32]), __uint_as_float(v1[2 * p - 31]));
-                                    z[p] = __ffma2_rn(s, l2e, lds_f32x2(er + p * 8));
-                                }
-                            }
-                            if (nv < grp * 16 + 16) {
-#pragma unroll
-                                for (int p = grp * 8; p < grp * 8 + 8; ++p) {
-                                    if (2 * p >= nv) z[p].x = -INFINITY;
-                                    if (2 * p + 1 >= nv) z[p].y = -INFINITY;
-                                }
+                            for (int p = 0; p < 16; ++p) {
+                                z[p] = __ffma2_rn(make_float2(__uint_as_float(v0[2 * p]), __uint_as_float(v0[2 * p + 1])), l2e, e2);
+                                z[16 + p] = __ffma2_rn(make_float2(__uint_as_float(v1[2 * p]), __uint_as_float(v1[2 * p + 1])), l2e, e2);
                             }
                         } else {
 #pragma unroll
-                            for (int p = grp * 8; p < grp * 8 + 8; ++p) z[p] = make_float2(-INFINITY, -INFINITY);
+                            for (int p = 0; p < 16; ++p) {
+                                z[p] = __ffma2_rn(make_float2(__uint_as_float(v0[2 * p]), __uint_as_float(v0[2 * p + 1])), l2e,
+                                                  lds_f32x2(er + p * 8));
+                                z[16 + p] = __ffma2_rn(make_float2(__uint_as_float(v1[2 * p]), __uint_as_float(v1[2 * p + 1])), l2e,
+                                                       lds_f32x2(er + (16 + p) * 8));
+                            }
+                        }
+                    } else {
+                        // an item's last tile: 16-column groups that are whole, cut by the sequence end, or absent (the
+                        // tensor core computed only the first ceil16(nv) columns)
+                        uint32_t v0[32], v1[32];
+                        ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN, v0);
+                        if (nv > 32) ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN + 32, v1);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int grp = 0; grp < 4; ++grp) {
+                            if (grp * 16 < nv) {
+#pragma unroll
+                                for (int p = grp * 8; p < grp * 8 + 8; ++p) {
+                                    const float2 sc = p < 16 ? make_float2(__uint_as_float(v0[2 * p]), __uint_as_float(v0[2 * p + 1]))
+                                                             : make_float2(__uint_as_float(v1[2 * p - 32]), __uint_as_float(v1[2 * p - 31]));
+                                    // (the table is read only for tiles near the diagonal: it is not addressable for far ones)
+                                    const float2 e2 = bias_const ? make_float2(e_c, e_c) : lds_f32x2(bias_const ? es : er + p * 8);
+                                    z[p] = __ffma2_rn(sc, l2e, e2);
+                                    if (2 * p >= nv) z[p].x = -INFINITY;
+                                    if (2 * p + 1 >= nv) z[p].y = -INFINITY;
+                                }
+                            } else {
+#pragma unroll
+                                for (int p = grp * 8; p < grp * 8 + 8; ++p) z[p] = make_float2(-INFINITY, -INFINITY);
+                            }
                         }
                     }
                     float mxa = z[0].x, mxb = z[0].y, mxc = z[1].x, mxd = z[1].y;  // four independent chains
@@ -388,27 +400,20 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                         }
                         ptx::tmem_st_wait();
                     }
+                    // P = 2^(z - m): columns masked above give 2^-inf = 0, so the exp pass needs no special cases
                     const float2 neg_m = make_float2(-m, -m);
                     float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int grp = 0; grp < 4; ++grp) {
-                        if (grp * 16 < nv) {
-#pragma unroll
-                            for (int p = grp * 8; p < grp * 8 + 8; p += 2) {
-                                float2 a = __fadd2_rn(z[p], neg_m), c2 = __fadd2_rn(z[p + 1], neg_m);
-                                a.x = ex2(a.x);
-                                a.y = ex2(a.y);
-                                c2.x = ex2(c2.x);
-                                c2.y = ex2(c2.y);
-                                s0 = __fadd2_rn(s0, a);
-                                s1 = __fadd2_rn(s1, c2);
-                                pk[p] = ptx::pack_h2_sat(a.x, a.y);
-                                pk[p + 1] = ptx::pack_h2_sat(c2.x, c2.y);
-                            }
-                        } else {
-#pragma unroll
-                            for (int p = grp * 8; p < grp * 8 + 8; ++p) pk[p] = 0u;
-                        }
+                    for (int p = 0; p < 32; p += 2) {
+                        float2 a = __fadd2_rn(z[p], neg_m), c2 = __fadd2_rn(z[p + 1], neg_m);
+                        a.x = ex2(a.x);
+                        a.y = ex2(a.y);
+                        c2.x = ex2(c2.x);
+                        c2.y = ex2(c2.y);
+                        s0 = __fadd2_rn(s0, a);
+                        s1 = __fadd2_rn(s1, c2);
+                        pk[p] = ptx::pack_h2_sat(a.x, a.y);
+                        pk[p + 1] = ptx::pack_h2_sat(c2.x, c2.y);
                     }
                     l += (s0.x + s0.y) + (s1.x + s1.y);
                 }

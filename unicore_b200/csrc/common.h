@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -20,6 +21,19 @@ enum : int {
     P5_ERR_NOMEM = 5,
     P5_ERR_UNSUPPORTED = 6,
 };
+
+// Experiment knobs (environment variables) exist only in the debug library (libprostt5_b200_debug.so, built with
+// -DP5_DEBUG_BUILD): the product library always takes the default, so no environment can make it skip work.
+#ifdef P5_DEBUG_BUILD
+inline int env_knob(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+inline bool env_flag(const char* name) { return getenv(name) != nullptr; }
+#else
+inline int env_knob(const char*, int dflt) { return dflt; }
+inline bool env_flag(const char*) { return false; }
+#endif
 
 struct Error : public std::runtime_error {
     int code;

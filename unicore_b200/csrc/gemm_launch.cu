@@ -5,6 +5,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -49,7 +50,7 @@ CUtensorMap make_kmajor_tensor_map(const void* ptr, uint64_t rows, uint64_t cols
     cuuint32_t box[2] = {kGemmBlockK, box_rows};
     cuuint32_t estr[2] = {1, 1};
     // P5_GEMM_PROMO (traffic experiments only): L2 promotion of operand loads, 0 none / 1 64 B / 2 128 B / 3 256 B
-    static const int promo = getenv("P5_GEMM_PROMO") ? atoi(getenv("P5_GEMM_PROMO")) : 3;
+    static const int promo = env_knob("P5_GEMM_PROMO", 3);
     const CUtensorMapL2promotion l2p = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
                                        : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                        : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
@@ -106,7 +107,7 @@ void launch_one(cudaStream_t stream, int num_sms, const CUtensorMap& ta, const C
     const uint32_t num_nt = (s.N + kBlockN - 1) / kBlockN;
     const uint32_t tiles = num_mt * num_nt;
     uint32_t clusters = static_cast<uint32_t>(num_sms / kCtaGroup);
-    static const uint32_t max_clusters = getenv("P5_GEMM_CLUSTERS") ? uint32_t(atoi(getenv("P5_GEMM_CLUSTERS"))) : 0u;  // experiment knob
+    static const uint32_t max_clusters = uint32_t(env_knob("P5_GEMM_CLUSTERS", 0));  // experiment knob (debug library only)
     if (max_clusters && max_clusters < clusters) clusters = max_clusters;
     if (tiles < clusters) clusters = tiles;
     if (clusters == 0) return;
@@ -119,8 +120,8 @@ void launch_one(cudaStream_t stream, int num_sms, const CUtensorMap& ta, const C
     // (profiles/r01/gemm_prefer_sweep.txt).  The grid is rounded down to a multiple of four pairs (72 of 74).
     // P5_GEMM_CLUSTER = 2 turns it off, 8 forces it for every shape; P5_GEMM_PREFER=0 makes 8 the regular dimension
     // (experiments).
-    static const int cluster_env = getenv("P5_GEMM_CLUSTER") ? atoi(getenv("P5_GEMM_CLUSTER")) : 0;
-    static const bool prefer = !(getenv("P5_GEMM_PREFER") && atoi(getenv("P5_GEMM_PREFER")) == 0);
+    static const int cluster_env = env_knob("P5_GEMM_CLUSTER", 0);
+    static const bool prefer = env_knob("P5_GEMM_PREFER", 1) != 0;
     uint32_t cluster_dim = kCtaGroup, preferred_dim = 0;
     const bool k_heavy = s.K >= 2048 && num_nt % 4 == 0 && num_nt <= 8;
     const uint32_t cluster_ctas = cluster_env ? uint32_t(cluster_env) : (k_heavy ? 8u : 2u);
@@ -161,8 +162,10 @@ void launch_one(cudaStream_t stream, int num_sms, const CUtensorMap& ta, const C
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    static bool preferred_ok = true;  // cleared if this driver rejects the attribute (it needs CUDA 12.8+)
-    if (preferred_dim && preferred_ok) {
+    // cleared (once, process-wide, with a message) if this driver rejects the attribute: it needs CUDA 12.8+.  The worker
+    // threads of several devices launch concurrently, hence the atomic.
+    static std::atomic<bool> preferred_ok{true};
+    if (preferred_dim && preferred_ok.load(std::memory_order_relaxed)) {
         attr[1].id = cudaLaunchAttributePreferredClusterDimension;
         attr[1].val.preferredClusterDim.x = preferred_dim;
         attr[1].val.preferredClusterDim.y = 1;
@@ -172,7 +175,8 @@ void launch_one(cudaStream_t stream, int num_sms, const CUtensorMap& ta, const C
         if (e == cudaSuccess) return;
         if (e != cudaErrorInvalidValue && e != cudaErrorNotSupported) P5_CUDA(e);
         (void)cudaGetLastError();  // the plain pair launch below computes the same thing
-        preferred_ok = false;
+        if (preferred_ok.exchange(false))
+            fprintf(stderr, "prostt5_b200: preferred cluster dimension rejected (%s); using plain CTA pairs\n", cudaGetErrorString(e));
         cfg.numAttrs = 1;
     }
     P5_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, tc, C, s));
@@ -231,16 +235,16 @@ void gemm_launch(cudaStream_t stream, int num_sms, int variant, Epi epi, const C
     P5_REQUIRE((ldc * (f16_out ? 2u : 4u)) % 16 == 0, P5_ERR_ARG, "GEMM ldc (%u) breaks 16-byte row alignment", ldc);
     P5_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0, P5_ERR_ARG, "GEMM output is not 16-byte aligned");
     static const uint32_t band = [] {
-        const char* e = getenv("P5_GEMM_BAND");
         // 1 = walk the N tiles of a row tile first: the CTA pairs running at the same time share the A rows and
         // every B tile is still read once per row tile.  Measured (ncu, config 2): same durations as bands of 2/8
         // row tiles, 18-30 % less DRAM read traffic on the FFN GEMMs.
-        const int v = e ? atoi(e) : 1;
+        const int v = env_knob("P5_GEMM_BAND", 1);
         return uint32_t(v >= 1 ? v : 1);
     }();
-    // P5_GEMM_BF16=1 (timing experiments only): interpret both operands as bf16 (a_format = b_format = 1)
-    static const uint32_t idesc_extra = (getenv("P5_GEMM_BF16") ? ((1u << 7) | (1u << 10)) : 0u) |
-                                        (getenv("P5_GEMM_NOSTORE") ? (1u << 31) : 0u);  // experiment: skip the epilogue stores
+    // Debug library only: P5_GEMM_BF16=1 interprets both operands as bf16 (a_format = b_format = 1), P5_GEMM_NOSTORE=1
+    // skips the epilogue stores (timing experiments).  In the product library both are compiled out (common.h).
+    static const uint32_t idesc_extra = (env_flag("P5_GEMM_BF16") ? ((1u << 7) | (1u << 10)) : 0u) |
+                                        (env_flag("P5_GEMM_NOSTORE") ? (1u << 31) : 0u);
     GemmShape s{M, N, K, ldc, band, idesc_extra};
     if (M == 0 || N == 0) return;
     switch (variant) {

@@ -63,6 +63,9 @@ void read_value(Cursor& c, uint32_t t, GgufValue& v) {
         v.arr_len = n;
         P5_REQUIRE(et != T_ARR, P5_ERR_FORMAT, "%s: nested GGUF arrays are not supported", c.path.c_str());
         if (et == T_STR) {
+            // every string takes at least its 8-byte length: a count beyond that is a corrupt file, not an allocation
+            P5_REQUIRE(n <= uint64_t(c.end - c.p) / 8, P5_ERR_FORMAT, "%s: corrupt GGUF string array (%llu entries)", c.path.c_str(),
+                       (unsigned long long)n);
             v.strs.reserve(n);
             for (uint64_t i = 0; i < n; ++i) v.strs.push_back(c.str());
         } else {
@@ -121,13 +124,24 @@ GgufFile::GgufFile(const std::string& path) : path_(path) {
         uint64_t align = meta_u64("general.alignment", 32);
         P5_REQUIRE(align >= 1 && align <= 4096, P5_ERR_FORMAT, "%s: bad alignment", path.c_str());
         uint64_t data_start = (uint64_t(c.p - map_) + align - 1) / align * align;
+        P5_REQUIRE(data_start <= size_, P5_ERR_FORMAT, "%s: tensor data starts beyond the file", path.c_str());
         for (auto& t : list) {
-            P5_REQUIRE(t.type == 0 || t.type == 1, P5_ERR_UNSUPPORTED,
-                       "%s: tensor %s has ggml type %u; only F32/F16 weights are supported (use prostt5-f16.gguf)",
-                       path.c_str(), t.name.c_str(), t.type);
-            P5_REQUIRE(data_start + t.offset + t.n_bytes() <= size_, P5_ERR_FORMAT, "%s: tensor %s exceeds the file",
-                       path.c_str(), t.name.c_str());
-            t.data = map_ + data_start + t.offset;
+            // Tensors of other ggml types (decoder tensors, BF16, quantised blocks) may sit in the file unused: they are
+            // recorded without data and only asking for one of them is an error (GgufFile::tensor).
+            t.supported = t.type == 0 || t.type == 1;
+            if (t.supported) {
+                // overflow-checked size: a corrupt shape must not wrap around and pass the bounds check
+                uint64_t n = 1;
+                bool ok = true;
+                for (uint64_t d : t.ne) {
+                    if (d != 0 && n > (uint64_t(1) << 62) / d) ok = false;
+                    n *= d;
+                }
+                const uint64_t esz = t.type == 1 ? 2 : 4, room = size_ - data_start;
+                ok = ok && n <= room / esz && t.offset <= room && n * esz <= room - t.offset;
+                P5_REQUIRE(ok, P5_ERR_FORMAT, "%s: tensor %s exceeds the file", path.c_str(), t.name.c_str());
+                t.data = map_ + data_start + t.offset;
+            }
             tensors_[t.name] = t;
         }
     } catch (...) {
@@ -162,6 +176,9 @@ std::string GgufFile::meta_str(const std::string& k, const std::string& dflt) co
 const GgufTensor& GgufFile::tensor(const std::string& name) const {
     auto it = tensors_.find(name);
     P5_REQUIRE(it != tensors_.end(), P5_ERR_FORMAT, "%s: tensor %s is missing", path_.c_str(), name.c_str());
+    P5_REQUIRE(it->second.supported, P5_ERR_UNSUPPORTED,
+               "%s: tensor %s has ggml type %u; only F32/F16 weights are supported (use prostt5-f16.gguf)", path_.c_str(),
+               name.c_str(), it->second.type);
     return it->second;
 }
 

@@ -12,9 +12,10 @@ namespace p5 {
 struct GgufTensor {
     std::string name;
     std::vector<uint64_t> ne;  // ggml order: ne[0] is the contiguous dimension
-    uint32_t type = 0;         // 0 = F32, 1 = F16
+    uint32_t type = 0;         // ggml type: 0 = F32, 1 = F16; anything else is recorded but cannot be read
     uint64_t offset = 0;       // from the start of the data section
     const uint8_t* data = nullptr;
+    bool supported = true;     // false: unused tensor of another ggml type (data == nullptr)
     uint64_t n_elements() const {
         uint64_t n = 1;
         for (uint64_t d : ne) n *= d;

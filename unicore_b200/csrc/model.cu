@@ -309,20 +309,20 @@ static const GgufTensor& cnn_tensor(const GgufFile& g, int which) {
     const GgufTensor *c0 = nullptr, *c1 = nullptr;
     for (const auto& kv : g.tensors()) {
         const GgufTensor& t = kv.second;
-        if (t.ne.size() != 3 || t.name.rfind("enc.", 0) == 0 || t.name.rfind("dec.", 0) == 0) continue;
+        if (!t.supported || t.ne.size() != 3 || t.name.rfind("enc.", 0) == 0 || t.name.rfind("dec.", 0) == 0) continue;
         if (t.ne[1] == d_model && !c0) c0 = &t;
     }
     if (c0)
         for (const auto& kv : g.tensors()) {
             const GgufTensor& t = kv.second;
-            if (t.ne.size() == 3 && &t != c0 && t.ne[1] == c0->ne[2] && t.ne[0] == c0->ne[0] && t.ne[2] <= 20 && !c1) c1 = &t;
+            if (t.supported && t.ne.size() == 3 && &t != c0 && t.ne[1] == c0->ne[2] && t.ne[0] == c0->ne[0] && t.ne[2] <= 20 && !c1) c1 = &t;
         }
     auto bias_of = [&](const GgufTensor* w) -> const GgufTensor* {
         if (!w) return nullptr;
         const std::string stem = w->name.substr(0, w->name.rfind('.'));  // "...weight" -> prefix
         for (const auto& kv : g.tensors()) {
             const GgufTensor& t = kv.second;
-            if (t.ne.size() == 1 && t.ne[0] == w->ne[2] && t.name.rfind(stem, 0) == 0 && t.name != w->name) return &t;
+            if (t.supported && t.ne.size() == 1 && t.ne[0] == w->ne[2] && t.name.rfind(stem, 0) == 0 && t.name != w->name) return &t;
         }
         return nullptr;
     };
@@ -347,10 +347,12 @@ void DeviceCtx::init(int device, const Model* m) {
     P5_CUDA(cudaEventCreate(&ev_end));
     for (auto& s : slots) P5_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     gemm_init_device();
-    attention_init_device();
     attention_tc_init_device();
+#ifdef P5_DEBUG_BUILD  // the A/B implementations live in the debug library only
+    attention_init_device();
     attention_tc2_init_device();
     attention_tc3_init_device();
+#endif
 }
 
 void DeviceCtx::load_weights(const GgufFile& g) {
@@ -441,9 +443,11 @@ void DeviceCtx::load_weights(const GgufFile& g) {
         std::vector<float> e(size_t(hp.n_head) * kAttnTcTable);
         attention_tc_build_table(m->bias_table.data(), hp.n_head, hp.max_distance, e.data());
         e_ext = upload<float>(e.data(), e.size() * 4);
+#ifdef P5_DEBUG_BUILD
         std::vector<float> e2(size_t(hp.n_head) * 2 * kAttnTcTable);
         attention_tc3_build_table(m->bias_table.data(), hp.n_head, hp.max_distance, e2.data());
         e_ext2 = upload<float>(e2.data(), e2.size() * 4);
+#endif
     }
     build_weight_maps();
 }
@@ -515,6 +519,9 @@ void DeviceCtx::ensure_workspace(uint32_t tokens) {
     // round up to whole CTA-pair row tiles so that TMA boxes never straddle the allocation
     const uint32_t n = (std::max(tokens, 256u) + 255u) / 256u * 256u;
     const size_t d = hp.d_model, inner = hp.d_inner(), ff = hp.d_ff;
+    // a failed allocation below (P5_ERR_NOMEM on a large batch) must not leave a capacity that later, smaller batches
+    // trust: the buffers are released one by one, so until all of them exist again the workspace is empty
+    cap = 0;
     h.alloc(n * d * 4);
     xn.alloc(n * d * 2);
     qkv.alloc(n * 3 * inner * 2);
@@ -586,15 +593,21 @@ void DeviceCtx::forward(const MetaLayout& l, const int32_t* meta_d, uint8_t* let
         const LayerW& L = layers[i];
         gemm(Epi::StoreF16, tm_xn, L.tm_qkv, qkv.p, 3 * inner, d);
         prof_begin(PC_ATTN);
+#ifdef P5_DEBUG_BUILD
         if (opt.attn_impl == 3 && e_ext2)
             launch_attention_tc3(stream, num_sms, tm_q, tm_kv, ctx.as<__half>(), aw128, l.n_aw128, e_ext2, hp.n_head, hp.max_distance);
         else if (opt.attn_impl == 2 && e_ext)
             launch_attention_tc2(stream, num_sms, tm_q, tm_kv, ctx.as<__half>(), aw128, l.n_aw128, e_ext, hp.n_head, hp.max_distance);
-        else if (opt.attn_impl == 1 && e_ext)
+        else if (opt.attn_impl == 0 || !e_ext)
+            launch_attention(stream, qkv.as<__half>(), ctx.as<__half>(), cu, aw, l.n_aw, bias, hp.n_head, hp.max_distance);
+        else
+#endif
+        {
+            P5_REQUIRE(e_ext != nullptr, P5_ERR_UNSUPPORTED, "relative attention max distance %u: the tcgen05 attention kernel assumes <= 128",
+                       hp.max_distance);
             launch_attention_tc(stream, num_sms, tm_q, tm_kv, tm_ctx_st, ctx.as<__half>(), aw128, l.n_aw128, e_ext, hp.n_head,
                                 hp.max_distance);
-        else
-            launch_attention(stream, qkv.as<__half>(), ctx.as<__half>(), cu, aw, l.n_aw, bias, hp.n_head, hp.max_distance);
+        }
         prof_end();
         gemm(Epi::AddF32, tm_ctx, L.tm_o, h.p, d, inner);
         prof_begin(PC_NORM);
@@ -681,6 +694,10 @@ Model* model_load(const std::string& dir, const int* devices, int n_devices) {
     expect_shape(g, c0, {hp.cnn_hidden, hp.d_model, hp.cnn_kernel});
     expect_shape(g, c1, {hp.cnn_classes, hp.cnn_hidden, hp.cnn_kernel});
     P5_REQUIRE(hp.d_kv == kHeadDim, P5_ERR_UNSUPPORTED, "attention head size %u: the kernels are specialised on 128", hp.d_kv);
+#ifndef P5_DEBUG_BUILD
+    P5_REQUIRE(hp.max_distance <= 128, P5_ERR_UNSUPPORTED,
+               "relative attention max distance %u: the tcgen05 attention kernel assumes <= 128 (ProstT5: 128)", hp.max_distance);
+#endif
     P5_REQUIRE(hp.d_model % 8 == 0 && hp.d_ff % 8 == 0 && hp.n_layer >= 1, P5_ERR_UNSUPPORTED, "unsupported model dimensions");
     P5_REQUIRE(hp.cnn_classes <= 20, P5_ERR_UNSUPPORTED, "the 3Di alphabet has 20 letters, the head has %u classes", hp.cnn_classes);
 
@@ -698,15 +715,10 @@ Model* model_load(const std::string& dir, const int* devices, int n_devices) {
     hp.x_id = find_tok(sp + "X");
     P5_REQUIRE(hp.prefix_id >= 0 && hp.eos_id >= 0 && hp.x_id >= 0, P5_ERR_FORMAT,
                "%s: vocabulary lacks <AA2fold>, </s> or the X residue token", path.c_str());
-    for (int b = 0; b < 256; ++b) {
-        int32_t id = hp.x_id;
-        int ch = (b >= 'a' && b <= 'z') ? b - 32 : b;
-        if (ch >= 'A' && ch <= 'Z' && ch != 'U' && ch != 'Z' && ch != 'O' && ch != 'B') {
-            const int32_t t = find_tok(sp + std::string(1, char(ch)));
-            if (t >= 0) id = t;
-        }
-        m->lut[b] = id;
-    }
+    // residue letter -> token id for all 26 letters (-1 = no such token in the vocabulary); the byte table the library
+    // tokenises with is derived from it and from the "map_rare_to_x" option
+    for (int ch = 'A'; ch <= 'Z'; ++ch) m->letter_tok[ch - 'A'] = find_tok(sp + std::string(1, char(ch)));
+    model_rebuild_token_table(*m);
     // relative-position bias by offset: bias[h][delta + max_distance] = rel[bucket(delta)][h]
     {
         auto rel = tensor_f32(tr);  // numpy shape [n_buckets, n_head]
@@ -781,6 +793,18 @@ static void device_worker(Model& m, DeviceCtx& c, const std::vector<Batch>& batc
     P5_CUDA(cudaSetDevice(c.dev));
     c.stats = Stats();
     c.ev_used = 0;
+    // A failure anywhere below (out of memory on a large batch, a launch error) must not leave a slot pointing into the
+    // caller's `batches`, which dies with this call: the next p5_predict would scatter through a dangling pointer.
+    struct SlotGuard {
+        DeviceCtx& c;
+        bool armed = true;
+        ~SlotGuard() {
+            if (!armed) return;
+            cudaStreamSynchronize(c.stream);  // nothing may still write the pinned buffers
+            c.slots[0].batch = c.slots[1].batch = nullptr;
+            c.ev_used = 0;
+        }
+    } guard{c};
     bool begun = false;
     size_t k = 0;
     for (;;) {
@@ -821,6 +845,7 @@ static void device_worker(Model& m, DeviceCtx& c, const std::vector<Batch>& batc
         c.stats.device_ms = ms;
     }
     c.collect_profile();
+    guard.armed = false;
 }
 
 template <class F>
@@ -951,6 +976,23 @@ void model_run_staged(Model& m, uint8_t* out) {
         }
     });
     m.last.attn_flops = attn_flops_of(m.hp, m.staged);
+}
+
+// byte -> token id.  Upper-cased residue letter -> "▁<letter>"; anything without a token -> "▁X".  U, Z, O, B:
+// ProstT5's published preprocessing (Rostlab predict_3Di_encoderOnly.py) maps them to X before tokenising (the
+// default); Foldseek's tokenizer may instead look up their own vocabulary entries (unverified), which
+// option "map_rare_to_x" = 0 reproduces.
+void model_rebuild_token_table(Model& m) {
+    for (int b = 0; b < 256; ++b) {
+        int32_t id = m.hp.x_id;
+        const int ch = (b >= 'a' && b <= 'z') ? b - 32 : b;
+        if (ch >= 'A' && ch <= 'Z') {
+            const bool rare = ch == 'U' || ch == 'Z' || ch == 'O' || ch == 'B';
+            const int32_t t = m.letter_tok[ch - 'A'];
+            if (t >= 0 && !(rare && m.opt.map_rare_to_x)) id = t;
+        }
+        m.lut[b] = id;
+    }
 }
 
 void model_rebuild_weight_maps(Model& m) {

@@ -80,7 +80,8 @@ struct Options {
     int head_include_eos = 1;
     int gemm_variant = 1;
     int profile = 0;
-    int attn_impl = 1;  // 1 = tcgen05 kernel, 0 = mma.sync kernel
+    int attn_impl = 1;  // 1 = the product's tcgen05 kernel; 0, 2, 3 = A/B kernels of the debug library
+    int map_rare_to_x = 1;  // U, Z, O, B tokenise as X (ProstT5's published preprocessing); 0 = their own tokens
 };
 
 class DeviceCtx;  // model.cu
@@ -89,6 +90,7 @@ struct Model {
     Hyper hp;
     Options opt;
     int32_t lut[256];
+    int32_t letter_tok[26];  // token id of "▁A".."▁Z", -1 if absent
     std::vector<float> bias_table;  // [n_head][2*max_distance+1], natural-log domain
     std::vector<std::unique_ptr<DeviceCtx>> devs;
     Stats last;
@@ -107,6 +109,7 @@ void model_predict(Model& m, const uint8_t* aa, const uint64_t* offsets, uint64_
 void model_stage(Model& m, const uint8_t* aa, const uint64_t* offsets, uint64_t n_seq, uint32_t split_len);
 void model_run_staged(Model& m, uint8_t* out);
 void model_rebuild_weight_maps(Model& m);  // after opt.gemm_variant changed
+void model_rebuild_token_table(Model& m);  // after opt.map_rare_to_x changed
 void model_encode_debug(Model& m, const uint8_t* aa, uint32_t len, float* hidden, float* logits, uint8_t* letters);
 
 // planning helpers (host only; also exercised by the CPU tests through the C ABI)

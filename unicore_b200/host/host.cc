@@ -633,6 +633,19 @@ struct ChildWatch {  // a rank that dies would leave the others waiting inside N
 };
 }  // namespace
 
+static void apply_options(p5_model* m, const PredictOptions& opt, const std::vector<Record>& recs, bool talk) {
+    if (opt.max_batch_tokens > 0 && p5_set_option(m, "max_batch_tokens", opt.max_batch_tokens) != 0)
+        die(ERR_GENERAL, p5_last_error());
+    if (opt.map_rare_to_x >= 0 && p5_set_option(m, "map_rare_to_x", opt.map_rare_to_x) != 0) die(ERR_GENERAL, p5_last_error());
+    if (!talk) return;
+    size_t n_long = 0;
+    for (const Record& r : recs) n_long += opt.split_len > 0 && r.seq.size() > opt.split_len;
+    if (n_long)
+        msg(3, std::to_string(n_long) + " sequences are longer than " + std::to_string(opt.split_len) +
+                   " residues and are predicted in chunks of that length (Foldseek's --prostt5-split-length default, which the "
+                   "reference relies on; --split-len 0 / --prostt5-split-length 0 predicts them in one piece)");
+}
+
 std::vector<std::string> predict_3di(const std::string& model_dir, const std::vector<Record>& recs,
                                      const PredictOptions& opt) {
     using clk = std::chrono::steady_clock;
@@ -713,7 +726,7 @@ std::vector<std::string> predict_3di(const std::string& model_dir, const std::ve
         if (rc != 0) fail("ProstT5 model: " + load_err);
         if (!comm_err.empty()) fail("NCCL communicator: " + comm_err);
         const auto t1 = clk::now();
-        if (opt.max_batch_tokens > 0 && p5_set_option(m, "max_batch_tokens", opt.max_batch_tokens) != 0) fail(p5_last_error());
+        apply_options(m, opt, recs, rank == 0);
         std::vector<uint64_t> off(recs.size() + 1, 0);
         for (size_t i = 0; i < recs.size(); ++i) off[i + 1] = off[i] + recs[i].seq.size();
         std::string aa;
@@ -757,8 +770,7 @@ std::vector<std::string> predict_3di(const std::string& model_dir, const std::ve
     if (p5_model_load(model_dir.c_str(), devs.empty() ? nullptr : devs.data(), devs.empty() ? -1 : int(devs.size()), &m) != 0)
         die(ERR_GENERAL, std::string("ProstT5 model: ") + p5_last_error());
     const auto t1 = clk::now();
-    if (opt.max_batch_tokens > 0 && p5_set_option(m, "max_batch_tokens", opt.max_batch_tokens) != 0)
-        die(ERR_GENERAL, p5_last_error());
+    apply_options(m, opt, recs, true);
     std::vector<uint64_t> off(recs.size() + 1, 0);
     for (size_t i = 0; i < recs.size(); ++i) off[i + 1] = off[i] + recs[i].seq.size();
     std::string aa;

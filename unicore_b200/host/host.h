@@ -101,7 +101,11 @@ std::vector<std::string> list_files_with_ext(const std::string& dir, const std::
 struct PredictOptions {
     std::vector<int> devices;  // empty = every visible device
     int procs = 0;             // > 1: one process per GPU (fork), count-sharding + one NCCL all-gather
-    uint32_t split_len = 0;
+    // Foldseek's own default applies in the reference, which passes no split flag [REF src/modules/createdb.rs:158-166]:
+    // --prostt5-split-length is believed to default to 1024 (unverified here): longer sequences are
+    // predicted in consecutive chunks.  0 = never split (full-length attention).
+    uint32_t split_len = 1024;
+    int map_rare_to_x = -1;  // -1 = library default (U, Z, O, B -> X)
     int64_t max_batch_tokens = 0;  // 0 = library default
     std::string stats_json;        // optional path
 };

@@ -30,7 +30,9 @@ static const char* kUsage =
     "      --devices <LIST>          Comma-separated CUDA devices (default: all visible)\n"
     "      --procs <N>               One process per GPU on N GPUs: sequences sharded by count, one NCCL all-gather of\n"
     "                                the 3Di strings, this process writes the DB (default: threads in one process)\n"
-    "      --split-len <N>           Predict sequences longer than N residues in chunks of N (default 0: never)\n"
+    "      --split-len <N>           Predict sequences longer than N residues in chunks of N [default: 1024, Foldseek's\n"
+    "                                --prostt5-split-length default, which the reference relies on]; 0 = never split\n"
+    "      --rare-residues <x|own>   U, Z, O, B tokenise as X (default, ProstT5's preprocessing) or as their own tokens\n"
     "      --max-batch-tokens <N>    Tokens per forward pass\n"
     "      --stats-json <PATH>       Write throughput counters as JSON\n";
 
@@ -64,6 +66,7 @@ static int createdb(int argc, char** argv) {
                 s = e + 1;
             }
         } else if (a == "--procs") popt.procs = atoi(value("procs").c_str());
+        else if (a == "--rare-residues") popt.map_rare_to_x = value("rare_residues") == "own" ? 0 : 1;
         else if (a == "--split-len") popt.split_len = uint32_t(atol(value("split_len").c_str()));
         else if (a == "--max-batch-tokens") popt.max_batch_tokens = atol(value("max_batch_tokens").c_str());
         else if (a == "--stats-json") popt.stats_json = value("stats_json");

@@ -84,8 +84,9 @@ class Comm:
 
 
 class Predictor:
-    def __init__(self, model_dir: str, devices: Sequence[int] | None = None):
-        self._lib = _lib.load()
+    def __init__(self, model_dir: str, devices: Sequence[int] | None = None, debug: bool = False):
+        """debug=True binds libprostt5_b200_debug.so (A/B kernels selectable through "attn_impl"; tests and tools only)."""
+        self._lib = _lib.load_debug() if debug else _lib.load()
         self._h = C.c_void_p()
         devs = list(devices) if devices is not None else [0]
         arr = (C.c_int * len(devs))(*devs)
