@@ -204,10 +204,17 @@ _REAL_STDOUT = sys.stdout
 
 
 def git_head():
+    """Commit of the tree (here) or of the build that travelled to the GPU box (unicore_b200/lib/BUILD_COMMIT)."""
     try:
-        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True,
-                              timeout=5).stdout.strip() or None
+        head = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True,
+                              timeout=5).stdout.strip()
+        if head:
+            return head
     except Exception:  # noqa: BLE001
+        pass
+    try:
+        return open(os.path.join(ROOT, "unicore_b200", "lib", "BUILD_COMMIT")).read().strip() or None
+    except OSError:
         return None
 
 

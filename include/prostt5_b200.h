@@ -71,7 +71,8 @@ int p5_bias_table(const p5_model* m, uint32_t head, float* out);
  *   "map_rare_to_x"     1 (default): U, Z, O, B tokenise as X, as ProstT5's published preprocessing does; 0: they take
  *                       their own vocabulary tokens (what a plain vocabulary lookup would do; which of the two Foldseek
  *                       does is unverified here, tools/compare_with_foldseek.sh reports both)
- *   "gemm_variant"      1 (default) CTA-pair tcgen05 GEMM, 0 single-CTA
+ *   "gemm_variant"      1: the CTA-pair tcgen05 GEMM (the only one in this library; the single-CTA variant 0 exists in
+ *                       libprostt5_b200_debug.so)
  *   "attn_impl"         1: the tcgen05 attention kernel (the only one in this library; the A/B implementations
  *                       0 = mma.sync, 2, 3 exist in libprostt5_b200_debug.so)
  *   "profile"           1: time every kernel class with CUDA events on the launch stream (p5_get_stats) */

@@ -10,6 +10,14 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with `-m gpu` on the GPU box)")
+    # Some tests use torch (device count, gloo workers) and some make the library bind NCCL (dlopen of libnccl.so.2).
+    # torch bundles a newer NCCL than the system's and needs ITS copy: import torch first, so that the library's dlopen
+    # by soname finds the copy already loaded instead of pinning the older system one for the whole process.  (A
+    # process without torch - the C++ CLI - binds the system NCCL.)
+    try:
+        import torch  # noqa: F401
+    except Exception:  # noqa: BLE001
+        pass
     # built artefacts are git-ignored: build them once if a fresh checkout has none (nvcc cross-compiles without a GPU)
     need = [os.path.join(ROOT, "unicore_b200", "lib", "libprostt5_b200.so"),
             os.path.join(ROOT, "unicore_b200", "lib", "libprostt5_b200_debug.so"),

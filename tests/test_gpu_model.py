@@ -158,13 +158,15 @@ def test_staged_equals_streaming(tiny):
     tiny.set_option("max_batch_tokens", 92160)
 
 
-def test_gemm_variants_agree(tiny):
+def test_gemm_variants_agree(tiny, tiny_dir):
+    """The product's CTA-pair GEMM against the single-CTA variant of the debug library: same K order, same bits."""
     rng = np.random.default_rng(13)
     seqs = [random_protein(rng, 200) for _ in range(8)]
-    tiny.set_option("gemm_variant", 0)
     a = tiny.predict(seqs)
-    tiny.set_option("gemm_variant", 1)
-    assert tiny.predict(seqs) == a
+    with Predictor(tiny_dir, debug=True) as dbg:
+        assert dbg.predict(seqs) == a
+        dbg.set_option("gemm_variant", 0)
+        assert dbg.predict(seqs) == a
 
 
 def test_split_len(tiny):

@@ -110,7 +110,7 @@ def stage_tiny():
     d = synth.model_dir("/tmp/p5_tiny", spec.TINY, seed=7)
     om = O.load_gguf_model(os.path.join(d, spec.WEIGHT_FILE))
     rng = np.random.default_rng(1)
-    with Predictor(d) as p:
+    with Predictor(d, debug=True) as p:
         res = {"info": p.info, "cmp": compare(p, om, [b"MA", rand_seq(rng, 17), rand_seq(rng, 62), rand_seq(rng, 63),
                                                       rand_seq(rng, 350), rand_seq(rng, 1030)])}
         seqs = [rand_seq(rng, int(L)) for L in rng.integers(2, 300, 40)]
@@ -133,7 +133,7 @@ def stage_full():
     t1 = time.time()
     rng = np.random.default_rng(2)
     res = {"gguf_s": round(t1 - t0, 1)}
-    with Predictor(d) as p:
+    with Predictor(d, debug=True) as p:
         res["load_s"] = round(time.time() - t1, 1)
         om = O.load_gguf_model(os.path.join(d, spec.WEIGHT_FILE))
         res["cmp"] = compare(p, om, [rand_seq(rng, 40), rand_seq(rng, 350)])
@@ -146,7 +146,7 @@ def stage_bench():
     d = synth.model_dir("/tmp/p5_full", spec.FULL, seed=1)
     aa, offsets = spec.synthetic_proteome("config2")
     res = {}
-    with Predictor(d) as p:
+    with Predictor(d, debug=True) as p:
         for variant in (1, 0):
             p.set_option("gemm_variant", variant)
             p.set_option("profile", 1)

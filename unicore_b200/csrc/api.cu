@@ -84,7 +84,12 @@ extern "C" int p5_set_option(p5_model* h, const char* key, int64_t value) {
         } else if (k == "head_include_eos") {
             o.head_include_eos = value != 0;
         } else if (k == "gemm_variant") {
-            P5_REQUIRE(value == 0 || value == 1, P5_ERR_ARG, "gemm_variant must be 0 or 1");
+#ifdef P5_DEBUG_BUILD
+            P5_REQUIRE(value == 0 || value == 1, P5_ERR_ARG, "gemm_variant must be 0 (single CTA) or 1 (CTA pair)");
+#else
+            P5_REQUIRE(value == 1, P5_ERR_ARG, "gemm_variant: this library carries the CTA-pair tcgen05 GEMM (1) only; the "
+                                               "single-CTA variant 0 is in libprostt5_b200_debug.so");
+#endif
             if (o.gemm_variant != int(value)) {
                 o.gemm_variant = int(value);
                 model_rebuild_weight_maps(*h->m);

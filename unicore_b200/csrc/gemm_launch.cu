@@ -213,17 +213,19 @@ void init_variant() {
 
 // Per-device one-time setup (function attributes are per device): call with the device current.
 void gemm_init_device() {
+#ifdef P5_DEBUG_BUILD  // the single-CTA variant is an A/B implementation: debug library only
     init_variant<1, 256, 4>();
+#endif
     init_variant<2, 256, 6>();
-
 }
 
 uint32_t gemm_b_box_rows(int variant) {
     switch (variant) {
+#ifdef P5_DEBUG_BUILD
         case 0: return 256;  // 1 CTA, full 256-row B tile
+#endif
         case 1: return 128;  // CTA pair, each CTA loads half of the 256-row B tile
-
-        default: throw Error(P5_ERR_ARG, strf("unknown GEMM variant %d", variant));
+        default: throw Error(P5_ERR_ARG, strf("GEMM variant %d is not built into this library", variant));
     }
 }
 
@@ -248,10 +250,11 @@ void gemm_launch(cudaStream_t stream, int num_sms, int variant, Epi epi, const C
     GemmShape s{M, N, K, ldc, band, idesc_extra};
     if (M == 0 || N == 0) return;
     switch (variant) {
+#ifdef P5_DEBUG_BUILD
         case 0: launch_epi<1, 256, 4>(stream, num_sms, epi, tma_a, tma_b, C, s); break;
+#endif
         case 1: launch_epi<2, 256, 6>(stream, num_sms, epi, tma_a, tma_b, C, s); break;
-
-        default: throw Error(P5_ERR_ARG, strf("unknown GEMM variant %d", variant));
+        default: throw Error(P5_ERR_ARG, strf("GEMM variant %d is not built into this library", variant));
     }
 }
 
