@@ -44,6 +44,11 @@ int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, const int32
 /* RMSNorm in isolation (csrc/kernels.cu).  ids_host == NULL: xn = fp16(rmsnorm(h) * w) for
  * h_host [M, d] fp32, optionally also the fp32 value in f32_host.  ids_host != NULL: the layer-0 form, h = E[ids]
  * (embd_host [n_vocab, d] fp16) written to h_out_host [M, d] fp32 and normalised into xn_host [M, d] fp16. */
+/* Phase cycle counters of the softmax warps, filled by p5_dbg_attention with impl = 16 + (15 | 64): out16[0..11] (32 entries for the fourth kernel: pass a 32-entry buffer), see
+ * attention_tc.cu (kDbgProf). reset bit 0 clears them after the read;
+ * bit 1 selects the counters of the fourth kernel (impl 5), see attention_tc4.cu. */
+int p5_dbg_attention_profile(int device, uint64_t* out16, int reset);
+
 int p5_dbg_rmsnorm(int device, const int32_t* ids_host, const uint16_t* embd_host, uint32_t n_vocab, const float* h_host,
                    const float* w_host, float eps, uint32_t M, uint32_t d, float* h_out_host, uint16_t* xn_host,
                    float* f32_host);

@@ -136,8 +136,9 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         attention_tc_init_device();
         attention_tc2_init_device();
         attention_tc3_init_device();
+        attention_tc4_init_device();
         // impl 2 = second-generation tcgen05 kernel (two softmax warpgroups per item); impl 16 + f = tcgen05 kernel with feature mask f (attention_tc.cu), for A/B tests of the pipelining features
-        P5_REQUIRE((impl >= 0 && impl <= 3) || (impl >= 16 && impl < 32), P5_ERR_ARG,
+        P5_REQUIRE((impl >= 0 && impl <= 5) || (impl >= 16 && impl < 272), P5_ERR_ARG,
                    "impl must be 0 (mma.sync), 1 (tcgen05), 2 (tcgen05, two softmax warpgroups), 3 (tcgen05, packed-pair math) "
                    "or 16..31 (first tcgen05 kernel with an explicit feature mask)");
         const int features = impl >= 16 ? impl - 16 : -1;
@@ -147,11 +148,13 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         const size_t inner = size_t(n_head) * kHeadDim;
         std::vector<int2> work;   // mma.sync kernel: (seq, q0)
         std::vector<int4> work4;  // tcgen05 kernel: (tok0, T, q0, 0)
+        std::vector<int4> work8;  // tcgen05 kernel 4: (tok0, T, first row of the 256-row pair, 0); impl 5 = with phase counters
         for (uint32_t s = 0; s < n_seq; ++s) {
             const int T = cu_host[s + 1] - cu_host[s];
             P5_REQUIRE(T >= 1, P5_ERR_ARG, "empty sequence %u", s);
             for (int q = 0; q < T; q += int(kAttnBlockM)) work.push_back(make_int2(int(s), q));
             for (int q = 0; q < T; q += int(kAttnTcBlockM)) work4.push_back(make_int4(cu_host[s], T, q, 0));
+            for (int q = 0; q < T; q += int(kAttnPairM)) work8.push_back(make_int4(cu_host[s], T, q, 0));
         }
         const size_t Mpad = (size_t(M) + 255) / 256 * 256;  // TMA boxes may reach past the last sequence: zero rows
         std::vector<float> e_host(size_t(n_head) * kAttnTcTable);
@@ -162,7 +165,7 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         attention_tc3_build_table(bias_host, n_head, max_dist, e2_host.data());
         ScratchBuf e_ext2(e2_host.size() * 4);
         P5_CUDA(cudaMemcpy(e_ext2.p, e2_host.data(), e2_host.size() * 4, cudaMemcpyHostToDevice));
-        ScratchBuf qkv(Mpad * 3 * inner * 2), ctx(M * inner * 2), cu((n_seq + 1) * 4), wk(work.size() * sizeof(int2)), wk4(work4.size() * sizeof(int4)),
+        ScratchBuf qkv(Mpad * 3 * inner * 2), ctx(M * inner * 2), cu((n_seq + 1) * 4), wk(work.size() * sizeof(int2)), wk4(work4.size() * sizeof(int4)), wk8(work8.size() * sizeof(int4)),
             bias(size_t(n_head) * (2 * max_dist + 1) * 4);
         P5_CUDA(cudaMemset(qkv.p, 0, Mpad * 3 * inner * 2));
         P5_CUDA(cudaMemcpy(qkv.p, qkv_host, M * 3 * inner * 2, cudaMemcpyHostToDevice));
@@ -172,11 +175,18 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         P5_CUDA(cudaMemcpy(cu.p, cu_host, (n_seq + 1) * 4, cudaMemcpyHostToDevice));
         P5_CUDA(cudaMemcpy(wk.p, work.data(), work.size() * sizeof(int2), cudaMemcpyHostToDevice));
         P5_CUDA(cudaMemcpy(wk4.p, work4.data(), work4.size() * sizeof(int4), cudaMemcpyHostToDevice));
+        P5_CUDA(cudaMemcpy(wk8.p, work8.data(), work8.size() * sizeof(int4), cudaMemcpyHostToDevice));
         P5_CUDA(cudaMemcpy(bias.p, bias_host, size_t(n_head) * (2 * max_dist + 1) * 4, cudaMemcpyHostToDevice));
         P5_CUDA(cudaMemset(ctx.p, 0, M * inner * 2));
         cudaStream_t st;
         P5_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         auto run = [&] {
+            if (impl == 4 || impl == 5) {
+                launch_attention_tc4(st, prop.multiProcessorCount, tm_q, tm_kv, static_cast<__half*>(ctx.p),
+                                     static_cast<const int4*>(wk8.p), uint32_t(work8.size()),
+                                     static_cast<const float*>(e_ext.p), n_head, max_dist, impl == 5);
+                return;
+            }
             if (impl == 3) {
                 launch_attention_tc3(st, prop.multiProcessorCount, tm_q, tm_kv, static_cast<__half*>(ctx.p),
                                      static_cast<const int4*>(wk4.p), uint32_t(work4.size()),
@@ -218,6 +228,16 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
             cudaEventDestroy(e1);
         }
         cudaStreamDestroy(st);
+    });
+}
+
+extern "C" int p5_dbg_attention_profile(int device, uint64_t* out16, int reset) {
+    return guarded([&] {
+        P5_REQUIRE(out16 != nullptr, P5_ERR_ARG, "null buffer");
+        P5_CUDA(cudaSetDevice(device));
+        static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "counter width");
+        if (reset & 2) attention_tc4_read_profile(reinterpret_cast<unsigned long long*>(out16), (reset & 1) != 0);
+        else attention_tc_read_profile(reinterpret_cast<unsigned long long*>(out16), (reset & 1) != 0);
     });
 }
 

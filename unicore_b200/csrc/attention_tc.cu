@@ -55,6 +55,18 @@ constexpr uint32_t kStageBytes = 32 * 64;                                     //
 constexpr uint32_t kSmemBar = kSmemStage + 4 * kStageBytes;
 constexpr uint32_t kNumBars = 22;
 constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatBars = 8;
+// timing-only ablations (debug library; WRONG results): 16 = every tile takes the constant-bias path (no LDS of the
+// table), 32 = the exponentials are replaced by one FMUL each (no MUFU)
+constexpr uint32_t kAblNoTable = 16, kAblNoEx2 = 32;
+// 64 = phase cycle counters of the softmax warps (debug library): clock() deltas summed over all valid warps into
+// g_attn_prof: 0 wait S, 1 tcgen05.ld, 2 bias, 3 max + vote (+ rescale), 4 exp/sum/pack, 5 tcgen05.st + arrive,
+// 6 epilogue wait for P.V, 7 epilogue rest, 8 between items, 9 total, 10 warp-tiles, 11 warp-items
+constexpr uint32_t kDbgProf = 64;
+// 128 = timing-only: no softmax at all (P = 0 stored right after S arrives): the rate of the TMA/MMA pipeline alone
+constexpr uint32_t kAblNoMath = 128;
+#ifdef P5_DEBUG_BUILD
+__device__ unsigned long long g_attn_prof[16];
+#endif
 constexpr uint32_t kSmemTotal = kSmemBar + kNumBars * 8 + 16;
 constexpr uint32_t kSmemDynamic = kSmemTotal + 1024;  // slack for manual 1024 B alignment
 constexpr uint32_t kTmemCols = 256;                   // O: [0,128)  S/P buffer 0: [128,192)  buffer 1: [192,256)
@@ -106,6 +118,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     const float* __restrict__ e_ext) {
     constexpr bool kTable = (kF & kFeatTable) != 0, kDefer = (kF & kFeatDefer) != 0, kStore = (kF & kFeatStore) != 0,
                    kBars = (kF & kFeatBars) != 0;
+    constexpr bool kNoTable = (kF & kAblNoTable) != 0, kNoEx2 = (kF & kAblNoEx2) != 0, kProf = (kF & kDbgProf) != 0, kNoMath = (kF & kAblNoMath) != 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
@@ -278,14 +291,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         int cur_h = -1;
         uint32_t es = e_smem;
         float e_lo = 0.f, e_hi = 0.f;
+        uint32_t pc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // kProf
+        uint32_t tp = 0;
+        auto tick = [&](int slot) {
+            if constexpr (kProf) {
+                const uint32_t now = uint32_t(clock());
+                pc[slot] += now - tp;
+                tp = now;
+            }
+        };
+        if constexpr (kProf) tp = uint32_t(clock());
+        [[maybe_unused]] const uint32_t t_begin = tp;
 
         // O / l -> ctx for the item whose tiles ended at global tile index g_end (exclusive).
         //   row0 = first token row of this warp's 32 rows, valid = how many of them belong to the sequence
         auto epilogue = [&](float inv, int row0, int valid, int h, uint32_t g_end, uint32_t nt) {
             // the last two P.V (one per barrier) may both still be in flight: wait for both, older first
+            tick(5);
             if (nt >= 2) ptx::mbar_wait(&pv_done[(g_end - 2) & 1], ((g_end - 2) >> 1) & 1);
             ptx::mbar_wait(&pv_done[(g_end - 1) & 1], ((g_end - 1) >> 1) & 1);
             ptx::tc_fence_after();
+            tick(6);
             if (valid > 0) {
                 const bool use_tma = kStore && valid == 32;  // warp-uniform
                 __half* dst = ctx + size_t(row0 + int(lane)) * (size_t(H) * kD) + size_t(h) * kD;
@@ -319,6 +345,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(o_empty);
+            tick(7);
         };
         bool pend = false;  // kDefer: the previous item still owes its epilogue
         float p_inv = 0.f;
@@ -358,22 +385,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             for (uint32_t j = 0; j < it.nt; ++j, ++g) {
                 const uint32_t b = g & 1, ph = (g >> 1) & 1;
                 const int j0 = int(j * kBN);
+                tick(j == 0 ? 8 : 5);
                 ptx::mbar_wait(&s_full[b], ph);
                 ptx::tc_fence_after();
+                tick(0);
+                if constexpr (kProf) pc[10] += warp_valid ? 1u : 0u;
                 uint32_t pk[32];
-                if (!warp_valid) {  // all 32 query rows lie past the end of the sequence: keep the protocol going only
+                if (kNoMath || !warp_valid) {  // all 32 query rows lie past the end of the sequence: keep the protocol going only
 #pragma unroll
                     for (int c = 0; c < 32; ++c) pk[c] = 0u;
                 } else {
                 // bias: constant when the whole tile is beyond +-128 of the diagonal, table otherwise
                 const int dmin = j0 - (it.q0 + int(kBM) - 1), dmax = j0 + int(kBN) - 1 - it.q0;
-                const bool bias_const = dmax <= -128 || dmin >= 128;
+                const bool bias_const = kNoTable || dmax <= -128 || dmin >= 128;
                 const float e_c = dmax <= -128 ? e_lo : e_hi;
                 const uint32_t er = es + uint32_t(int(kEHalf) - row_seq + j0) * 4;
                 uint32_t v0[32], v1[32];
                 ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN, v0);
                 ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN + 32, v1);
                 ptx::tmem_ld_wait();
+                tick(1);
                 float z[64];
                 if (bias_const) {
                     const float e = e_c;
@@ -394,6 +425,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     for (int c = 0; c < 64; ++c)
                         if (j0 + c >= it.T) z[c] = -INFINITY;
                 }
+                tick(2);
                 float mxa = z[0], mxb = z[1], mxc = z[2], mxd = z[3];  // four independent chains
 #pragma unroll
                 for (int c = 4; c < 64; c += 4) {
@@ -426,16 +458,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     }
                     ptx::tmem_st_wait();
                 }
+                tick(3);
                 float sa = 0.f, sb = 0.f, sc = 0.f, sd = 0.f;
 #pragma unroll
                 for (int c = 0; c < 32; c += 2) {
-                    const float p0 = ex2(z[2 * c] - m), p1 = ex2(z[2 * c + 1] - m);
-                    const float p2 = ex2(z[2 * c + 2] - m), p3 = ex2(z[2 * c + 3] - m);
+                    float p0, p1, p2, p3;
+                    if constexpr (kNoEx2) {
+                        p0 = (z[2 * c] - m) * 0.001f; p1 = (z[2 * c + 1] - m) * 0.001f;
+                        p2 = (z[2 * c + 2] - m) * 0.001f; p3 = (z[2 * c + 3] - m) * 0.001f;
+                    } else {
+                        p0 = ex2(z[2 * c] - m); p1 = ex2(z[2 * c + 1] - m);
+                        p2 = ex2(z[2 * c + 2] - m); p3 = ex2(z[2 * c + 3] - m);
+                    }
                     sa += p0; sb += p1; sc += p2; sd += p3;
                     pk[c] = pack_h2(p0, p1);
                     pk[c + 1] = pack_h2(p2, p3);
                 }
                 l += (sa + sb) + (sc + sd);
+                tick(4);
                 }
                 ptx::tmem_st_32x32b_x32(t_lane + 128 + b * kBN, pk);  // P over the first 32 columns of S
                 ptx::tmem_st_wait();
@@ -469,6 +509,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if constexpr (kStore) {
             if (lane == 0) ptx::bulk_wait<0>();  // all stores of this warp have completed before the CTA retires
         }
+#ifdef P5_DEBUG_BUILD
+        if constexpr (kProf) {
+            pc[9] = uint32_t(clock()) - t_begin;
+            pc[11] = n;
+            if (lane == 0)
+                for (int i = 0; i < 12; ++i) atomicAdd(&g_attn_prof[i], (unsigned long long)pc[i]);
+        }
+#endif
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -491,6 +539,12 @@ AttnKernel attn_kernel(uint32_t feat) {
         case 7: return attention_tc_kernel<7>;
         case 8: return attention_tc_kernel<8>;
         case 14: return attention_tc_kernel<14>;
+        case 15 + 16: return attention_tc_kernel<15 + 16>;
+        case 15 + 32: return attention_tc_kernel<15 + 32>;
+        case 15 + 48: return attention_tc_kernel<15 + 48>;
+        case 15 + 64: return attention_tc_kernel<15 + 64>;
+        case 15 + 128: return attention_tc_kernel<15 + 128>;
+        case 15 + 192: return attention_tc_kernel<15 + 192>;
 #endif
         default: throw Error(P5_ERR_ARG, strf("attention feature mask %u is not built", feat));
     }
@@ -499,7 +553,7 @@ AttnKernel attn_kernel(uint32_t feat) {
 
 void attention_tc_init_device() {
 #ifdef P5_DEBUG_BUILD
-    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u})
+    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u, 31u, 47u, 63u, 79u, 143u, 207u})
 #else
     for (uint32_t f : {15u})
 #endif
@@ -516,6 +570,16 @@ void attention_tc_build_table(const float* bias, uint32_t H, uint32_t max_dist, 
             e_ext[size_t(h) * kEPad + i] = bias[size_t(h) * (2 * max_dist + 1) + size_t(d + int(max_dist))] * kLog2e;
         }
 }
+
+#ifdef P5_DEBUG_BUILD
+void attention_tc_read_profile(unsigned long long* out16, bool reset) {
+    P5_CUDA(cudaMemcpyFromSymbol(out16, g_attn_prof, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {};
+        P5_CUDA(cudaMemcpyToSymbol(g_attn_prof, z, sizeof(z)));
+    }
+}
+#endif
 
 int attention_tc_default_features() {
     static const int f = env_knob("P5_ATTN_FEAT", 15);  // experiment knob (debug library only)

@@ -37,6 +37,7 @@ constexpr uint32_t kAttnTcTable = 644;
 void attention_tc_init_device();
 void attention_tc_build_table(const float* bias, uint32_t H, uint32_t max_dist, float* e_ext);
 CUtensorMap make_attn_store_tensor_map(void* ctx, uint64_t rows, uint64_t cols);  // box 32 rows x 32 columns, 64B swizzle
+void attention_tc_read_profile(unsigned long long* out16, bool reset);  // debug library only (feature bit 64)
 void launch_attention_tc(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, const CUtensorMap& tm_kv,
                          const CUtensorMap& tm_ctx, __half* ctx, const int4* work128, uint32_t n_work,
                          const float* e_ext, uint32_t H, uint32_t max_dist, int features = -1);
@@ -54,6 +55,16 @@ void attention_tc3_init_device();
 void attention_tc3_build_table(const float* bias, uint32_t H, uint32_t max_dist, float* e_ext2);
 void launch_attention_tc3(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, const CUtensorMap& tm_kv, __half* ctx,
                           const int4* work128, uint32_t n_work, const float* e_ext2, uint32_t H, uint32_t max_dist);
+
+// Fourth tcgen05 kernel (attention_tc4.cu): one CTA per SM, two 128-row query tiles of one sequence sharing one K/V
+// stream (four-stage ring), one-pass softmax against the running reference maximum; work256[n_work] = (first token of
+// the sequence, its token count, first query row of the 256-row pair, 0); e_ext as for the first kernel.
+constexpr uint32_t kAttnPairM = 256;
+void attention_tc4_init_device();
+void attention_tc4_read_profile(unsigned long long* out16, bool reset);  // debug library only
+void launch_attention_tc4(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, const CUtensorMap& tm_kv, __half* ctx,
+                          const int4* work256, uint32_t n_work, const float* e_ext, uint32_t H, uint32_t max_dist,
+                          bool profile = false);
 
 constexpr uint32_t kAttnBlockM = 64;  // query rows per attention work item
 constexpr uint32_t kHeadChunk = 64;   // residues per head work item

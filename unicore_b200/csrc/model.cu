@@ -80,13 +80,14 @@ double unit_flops(const Hyper& hp, uint32_t len) {  // SURVEY.md §8d F_seq(L)
 static void finish_layout(Batch& b) {
     MetaLayout& l = b.lay;
     l.S = uint32_t(b.units.size());
-    l.M = 0; l.n_res = 0; l.n_aw = 0; l.n_aw128 = 0; l.n_hw = 0;
+    l.M = 0; l.n_res = 0; l.n_aw = 0; l.n_aw128 = 0; l.n_aw256 = 0; l.n_hw = 0;
     for (const Unit& u : b.units) {
         const uint32_t T = u.len + 2;
         l.M += T;
         l.n_res += u.len;
         l.n_aw += (T + kAttnBlockM - 1) / kAttnBlockM;
         l.n_aw128 += (T + kAttnTcBlockM - 1) / kAttnTcBlockM;
+        l.n_aw256 += (T + kAttnPairM - 1) / kAttnPairM;
         l.n_hw += (u.len + kHeadChunk - 1) / kHeadChunk;
     }
     auto align4 = [](uint32_t w) { return (w + 3u) & ~3u; };  // 16-byte aligned sub-blocks
@@ -94,7 +95,8 @@ static void finish_layout(Batch& b) {
     l.off_cu = align4(l.M);
     l.off_aw = l.off_cu + align4(l.S + 1);
     l.off_aw128 = l.off_aw + align4(2 * l.n_aw);
-    l.off_hw = l.off_aw128 + 4 * l.n_aw128;
+    l.off_aw256 = l.off_aw128 + 4 * l.n_aw128;
+    l.off_hw = l.off_aw256 + 4 * l.n_aw256;
     l.words = l.off_hw + align4(2 * l.n_hw);
 }
 
@@ -148,8 +150,9 @@ static void build_meta(const Model& m, const Batch& b, const uint8_t* aa, int32_
     int32_t* cu = w + l.off_cu;
     int32_t* aw = w + l.off_aw;
     int32_t* aw2 = w + l.off_aw128;
+    int32_t* aw3 = w + l.off_aw256;
     int32_t* hw = w + l.off_hw;
-    uint32_t tok = 0, na = 0, na2 = 0, nh = 0;
+    uint32_t tok = 0, na = 0, na2 = 0, na3 = 0, nh = 0;
     for (uint32_t s = 0; s < l.S; ++s) {
         const Unit& u = b.units[s];
         cu[s] = int32_t(tok);
@@ -162,6 +165,10 @@ static void build_meta(const Model& m, const Batch& b, const uint8_t* aa, int32_
         for (uint32_t q = 0; q < T; q += kAttnTcBlockM) {
             aw2[4 * na2] = cu[s]; aw2[4 * na2 + 1] = int32_t(T); aw2[4 * na2 + 2] = int32_t(q); aw2[4 * na2 + 3] = 0;
             ++na2;
+        }
+        for (uint32_t q = 0; q < T; q += kAttnPairM) {
+            aw3[4 * na3] = cu[s]; aw3[4 * na3 + 1] = int32_t(T); aw3[4 * na3 + 2] = int32_t(q); aw3[4 * na3 + 3] = 0;
+            ++na3;
         }
         for (uint32_t r = 0; r < u.len; r += kHeadChunk) { hw[2 * nh] = int32_t(s); hw[2 * nh + 1] = int32_t(r); ++nh; }
     }
@@ -352,6 +359,7 @@ void DeviceCtx::init(int device, const Model* m) {
     attention_init_device();
     attention_tc2_init_device();
     attention_tc3_init_device();
+    attention_tc4_init_device();
 #endif
 }
 
@@ -578,6 +586,7 @@ void DeviceCtx::forward(const MetaLayout& l, const int32_t* meta_d, uint8_t* let
     const int32_t* cu = meta_d + l.off_cu;
     const int2* aw = reinterpret_cast<const int2*>(meta_d + l.off_aw);
     const int4* aw128 = reinterpret_cast<const int4*>(meta_d + l.off_aw128);
+    const int4* aw256 = reinterpret_cast<const int4*>(meta_d + l.off_aw256);
     const int2* hw = reinterpret_cast<const int2*>(meta_d + l.off_hw);
     auto gemm = [&](Epi epi, const CUtensorMap& ta, const CUtensorMap& tb, void* C, uint32_t N, uint32_t K) {
         prof_begin(PC_GEMM);
@@ -594,7 +603,9 @@ void DeviceCtx::forward(const MetaLayout& l, const int32_t* meta_d, uint8_t* let
         gemm(Epi::StoreF16, tm_xn, L.tm_qkv, qkv.p, 3 * inner, d);
         prof_begin(PC_ATTN);
 #ifdef P5_DEBUG_BUILD
-        if (opt.attn_impl == 3 && e_ext2)
+        if (opt.attn_impl == 4 && e_ext)
+            launch_attention_tc4(stream, num_sms, tm_q, tm_kv, ctx.as<__half>(), aw256, l.n_aw256, e_ext, hp.n_head, hp.max_distance);
+        else if (opt.attn_impl == 3 && e_ext2)
             launch_attention_tc3(stream, num_sms, tm_q, tm_kv, ctx.as<__half>(), aw128, l.n_aw128, e_ext2, hp.n_head, hp.max_distance);
         else if (opt.attn_impl == 2 && e_ext)
             launch_attention_tc2(stream, num_sms, tm_q, tm_kv, ctx.as<__half>(), aw128, l.n_aw128, e_ext, hp.n_head, hp.max_distance);

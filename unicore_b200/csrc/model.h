@@ -56,7 +56,7 @@ struct Unit {
 // layout (in int32 words) of a batch's metadata block: ids | cu | attention work | head work
 struct MetaLayout {
     uint32_t M = 0, S = 0, n_res = 0;
-    uint32_t off_ids = 0, off_cu = 0, off_aw = 0, n_aw = 0, off_aw128 = 0, n_aw128 = 0, off_hw = 0, n_hw = 0, words = 0;
+    uint32_t off_ids = 0, off_cu = 0, off_aw = 0, n_aw = 0, off_aw128 = 0, n_aw128 = 0, off_aw256 = 0, n_aw256 = 0, off_hw = 0, n_hw = 0, words = 0;
 };
 
 struct Batch {
