@@ -26,6 +26,12 @@
 //   kFeatBars   one tcgen05.commit per event instead of two: s_full doubles as "K slot free" and pv_done as
 //               "V slot free" (the producer waits on the same barriers as the softmax warps), 3 instead of 5
 //               commits per tile on the single MMA-issuing thread.
+//   kFeatOnePass  (debug library only, NOT in the default mask 15) every key tile after an item's first (and not cut by the
+//               end of the sequence) is ONE pass against the running reference maximum (attention_softmax.cuh: packed
+//               FFMA2 / FADD2 / FMNMX3 pairs, no separate bias and maximum passes); the two-pass code handles the first tile,
+//               the cut tile and the rescale, and the eight tiles after a redone one.  Measured (profiles/r02/README.md):
+//               +0.3 % on config 2, +2-3 % on ragged / long batches, -6 % on peaked scores: the two warps of a scheduler
+//               meet on the MUFU pipe in either form, so the product keeps the simpler two-pass softmax.
 // Tried and dropped (profiles/r01/README.md): streaming the softmax in 16-column chunks against the running
 // maximum, overlapping the next tile's tcgen05.ld with the P store, requesting K one tile ahead of V, and L2
 // prefetches (cp.async.bulk.prefetch.tensor) of the coming Q/K/V tiles.
@@ -34,6 +40,7 @@
 #include <cstdlib>
 
 #include "common.h"
+#include "attention_softmax.cuh"
 #include "gemm_launch.h"
 #include "ptx.cuh"
 
@@ -54,16 +61,16 @@ constexpr uint32_t kSmemStage = (kSmemE + 2 * kEPad * 4 + 511) / 512 * 512;  // 
 constexpr uint32_t kStageBytes = 32 * 64;                                     // 32 rows x 32 fp16 columns
 constexpr uint32_t kSmemBar = kSmemStage + 4 * kStageBytes;
 constexpr uint32_t kNumBars = 22;
-constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatBars = 8;
-// timing-only ablations (debug library; WRONG results): 16 = every tile takes the constant-bias path (no LDS of the
-// table), 32 = the exponentials are replaced by one FMUL each (no MUFU)
-constexpr uint32_t kAblNoTable = 16, kAblNoEx2 = 32;
-// 64 = phase cycle counters of the softmax warps (debug library): clock() deltas summed over all valid warps into
+constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatBars = 8, kFeatOnePass = 16;
+// timing-only ablations (debug library; WRONG results): 32 = every tile takes the constant-bias path (no LDS of the
+// table), 64 = the exponentials are replaced by one FMUL each (no MUFU)
+constexpr uint32_t kAblNoTable = 32, kAblNoEx2 = 64;
+// 128 = phase cycle counters of the softmax warps (debug library): clock() deltas summed over all valid warps into
 // g_attn_prof: 0 wait S, 1 tcgen05.ld, 2 bias, 3 max + vote (+ rescale), 4 exp/sum/pack, 5 tcgen05.st + arrive,
 // 6 epilogue wait for P.V, 7 epilogue rest, 8 between items, 9 total, 10 warp-tiles, 11 warp-items
-constexpr uint32_t kDbgProf = 64;
-// 128 = timing-only: no softmax at all (P = 0 stored right after S arrives): the rate of the TMA/MMA pipeline alone
-constexpr uint32_t kAblNoMath = 128;
+constexpr uint32_t kDbgProf = 128;
+// 256 = timing-only: no softmax at all (P = 0 stored right after S arrives): the rate of the TMA/MMA pipeline alone
+constexpr uint32_t kAblNoMath = 256;
 #ifdef P5_DEBUG_BUILD
 __device__ unsigned long long g_attn_prof[16];
 #endif
@@ -72,6 +79,7 @@ constexpr uint32_t kSmemDynamic = kSmemTotal + 1024;  // slack for manual 1024 B
 constexpr uint32_t kTmemCols = 256;                   // O: [0,128)  S/P buffer 0: [128,192)  buffer 1: [192,256)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays below 2^8 between rescales
+constexpr uint32_t kOnePassCoolDown = 8;   // key tiles without the one-pass attempt after a redone tile
 constexpr float kHeadRoom = 6.0f;          // log2 units added to the first tile's row max: P starts at <= 2^-6 and
                                            // rescales of the accumulator become rare (they were 23 % of the tiles)
 
@@ -117,7 +125,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     const int4* __restrict__ work, uint32_t n_work, uint32_t n_items, uint32_t H,
                     const float* __restrict__ e_ext) {
     constexpr bool kTable = (kF & kFeatTable) != 0, kDefer = (kF & kFeatDefer) != 0, kStore = (kF & kFeatStore) != 0,
-                   kBars = (kF & kFeatBars) != 0;
+                   kBars = (kF & kFeatBars) != 0, kOnePass = (kF & kFeatOnePass) != 0;
     constexpr bool kNoTable = (kF & kAblNoTable) != 0, kNoEx2 = (kF & kAblNoEx2) != 0, kProf = (kF & kDbgProf) != 0, kNoMath = (kF & kAblNoMath) != 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -381,6 +389,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             }
             const int row_seq = it.q0 + int(r);
             float m = -INFINITY, l = 0.f;
+            [[maybe_unused]] uint32_t cool = 0;  // per item: the path a tile takes depends on this sequence's scores only
             const bool warp_valid = it.q0 + int(warp * 32) < it.T;
             for (uint32_t j = 0; j < it.nt; ++j, ++g) {
                 const uint32_t b = g & 1, ph = (g >> 1) & 1;
@@ -405,6 +414,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN + 32, v1);
                 ptx::tmem_ld_wait();
                 tick(1);
+                bool two_pass = true;
+                if constexpr (kOnePass) {
+                    // (after a tile that had to be redone the next kOnePassCoolDown tiles of the item go straight to the
+                    // two-pass code: peaked scores, where the maximum keeps growing, must not pay for both paths)
+                    if (cool > 0) --cool;
+                    else if (j > 0 && j0 + int(kBN) <= it.T) {  // the reference maximum m is known and every column is a key
+                        float sum, dm;
+                        if (bias_const) softmax::tile_one_pass<false, false>(v0, v1, er, e_c, m, int(kBN), pk, sum, dm);
+                        else softmax::tile_one_pass<true, false>(v0, v1, er, e_c, m, int(kBN), pk, sum, dm);
+                        // (rows past the end of the sequence must not take part in the vote: see below)
+                        if (!__any_sync(0xffffffffu, row_seq < it.T && dm > kRescaleThreshold)) {
+                            l += sum;
+                            two_pass = false;
+                        } else {
+                            cool = kOnePassCoolDown;
+                        }
+                        tick(4);
+                    }
+                }
+                if (two_pass) {
                 float z[64];
                 if (bias_const) {
                     const float e = e_c;
@@ -477,6 +506,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 l += (sa + sb) + (sc + sd);
                 tick(4);
                 }
+                }
                 ptx::tmem_st_32x32b_x32(t_lane + 128 + b * kBN, pk);  // P over the first 32 columns of S
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
@@ -532,6 +562,7 @@ AttnKernel attn_kernel(uint32_t feat) {
     switch (feat) {  // the instantiated feature masks: the product library carries the default only
         case 15: return attention_tc_kernel<15>;
 #ifdef P5_DEBUG_BUILD
+        case 31: return attention_tc_kernel<31>;
         case 0: return attention_tc_kernel<0>;
         case 1: return attention_tc_kernel<1>;
         case 2: return attention_tc_kernel<2>;
@@ -539,12 +570,13 @@ AttnKernel attn_kernel(uint32_t feat) {
         case 7: return attention_tc_kernel<7>;
         case 8: return attention_tc_kernel<8>;
         case 14: return attention_tc_kernel<14>;
-        case 15 + 16: return attention_tc_kernel<15 + 16>;
         case 15 + 32: return attention_tc_kernel<15 + 32>;
-        case 15 + 48: return attention_tc_kernel<15 + 48>;
         case 15 + 64: return attention_tc_kernel<15 + 64>;
+        case 15 + 96: return attention_tc_kernel<15 + 96>;
         case 15 + 128: return attention_tc_kernel<15 + 128>;
-        case 15 + 192: return attention_tc_kernel<15 + 192>;
+        case 31 + 128: return attention_tc_kernel<31 + 128>;
+        case 15 + 256: return attention_tc_kernel<15 + 256>;
+        case 15 + 384: return attention_tc_kernel<15 + 384>;
 #endif
         default: throw Error(P5_ERR_ARG, strf("attention feature mask %u is not built", feat));
     }
@@ -553,7 +585,7 @@ AttnKernel attn_kernel(uint32_t feat) {
 
 void attention_tc_init_device() {
 #ifdef P5_DEBUG_BUILD
-    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u, 31u, 47u, 63u, 79u, 143u, 207u})
+    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u, 31u, 47u, 79u, 111u, 143u, 159u, 271u, 399u})
 #else
     for (uint32_t f : {15u})
 #endif

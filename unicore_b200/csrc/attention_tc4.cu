@@ -28,6 +28,7 @@
 #include "common.h"
 #include "gemm_launch.h"
 #include "kernels.h"
+#include "attention_softmax.cuh"
 #include "ptx.cuh"
 
 namespace p5 {
@@ -49,20 +50,11 @@ constexpr uint32_t kNumBars = 2 + 4 * kStages + 8 + 8 + 2 + 4;
 constexpr uint32_t kSmemTotal = kSmemBar + kNumBars * 8 + 16;
 constexpr uint32_t kSmemDynamic = kSmemTotal + 1024;  // slack for manual 1024 B alignment
 constexpr uint32_t kTmemCols = 512;  // tile X: O at X*256, S/P buffer b at X*256 + 128 + b*64
-constexpr float kLog2e = 1.4426950408889634f;
+using softmax::ex2;
+using softmax::kLog2e;
+using softmax::lds_f32;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays below 2^8 between rescales
 constexpr float kHeadRoom = 6.0f;          // log2 units added to the first tile's row max: P starts at <= 2^-6
-
-__device__ __forceinline__ float ex2(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ void stg_v8(void* p, const uint32_t* v) {  // 32 bytes = one sector, one instruction
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
                  "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -90,85 +82,8 @@ __device__ __forceinline__ Item get_item(uint32_t item, uint32_t n_work, const i
 }
 
 
-// z = S * log2(e) + bias for the column pair (c, c + 1) of a row; kTable: bias from the row's window of the shared-memory
-// table (er = address of the entry of column 0), else the constant e_c (tile further than 128 from the diagonal)
-template <bool kTable>
-__device__ __forceinline__ float2 score_pair(uint32_t s_lo, uint32_t s_hi, uint32_t er, float2 e2, int c) {
-    const float2 l2e = make_float2(kLog2e, kLog2e);
-    if constexpr (kTable) e2 = make_float2(lds_f32(er + c * 4), lds_f32(er + c * 4 + 4));
-    return __ffma2_rn(make_float2(__uint_as_float(s_lo), __uint_as_float(s_hi)), l2e, e2);
-}
-
-// Row maximum of z over the first nv columns of the tile (the pre-pass of an item's first key tile).
-template <bool kTable, bool kMasked>
-__device__ __forceinline__ float tile_row_max(const uint32_t (&v0)[32], const uint32_t (&v1)[32], uint32_t er, float e_c, int nv) {
-    const float2 e2 = make_float2(e_c, e_c);
-    float mxa = -INFINITY, mxb = -INFINITY;
-#pragma unroll
-    for (int p = 0; p < 16; ++p) {
-        if (!kMasked || 2 * p < nv) {
-            float2 a = score_pair<kTable>(v0[2 * p], v0[2 * p + 1], er, e2, 2 * p);
-            if (kMasked && 2 * p + 1 >= nv) a.y = -INFINITY;
-            mxa = fmaxf(fmaxf(mxa, a.x), a.y);
-        }
-        if (!kMasked || 32 + 2 * p < nv) {
-            float2 c2 = score_pair<kTable>(v1[2 * p], v1[2 * p + 1], er, e2, 32 + 2 * p);
-            if (kMasked && 32 + 2 * p + 1 >= nv) c2.y = -INFINITY;
-            mxb = fmaxf(fmaxf(mxb, c2.x), c2.y);
-        }
-    }
-    return fmaxf(mxa, mxb);
-}
-
-// One pass over a key tile against the known reference maximum m: P = 2^(z - m) packed to fp16 pairs, row sum, and the
-// largest z - m seen (the caller redoes the tile with a rescale if it exceeds the threshold).  Columns >= nv give P = 0.
-template <bool kTable, bool kMasked>
-__device__ __forceinline__ void tile_one_pass(const uint32_t (&v0)[32], const uint32_t (&v1)[32], uint32_t er, float e_c, float m,
-                                              int nv, uint32_t (&pk)[32], float& sum, float& dmax) {
-    // constant bias: z - m in one FFMA2; table: the bias pair minus m first (same instruction count as subtracting after)
-    const float2 neg_m = make_float2(-m, -m);
-    const float2 e2 = make_float2(e_c - m, e_c - m);
-    float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
-    float mxa = -INFINITY, mxb = -INFINITY;
-    const float2 l2e = make_float2(kLog2e, kLog2e);
-#pragma unroll
-    for (int p = 0; p < 16; ++p) {
-        if (!kMasked || 2 * p < nv) {
-            float2 a;
-            if constexpr (kTable)
-                a = __ffma2_rn(make_float2(__uint_as_float(v0[2 * p]), __uint_as_float(v0[2 * p + 1])), l2e,
-                               __fadd2_rn(make_float2(lds_f32(er + p * 8), lds_f32(er + p * 8 + 4)), neg_m));
-            else
-                a = __ffma2_rn(make_float2(__uint_as_float(v0[2 * p]), __uint_as_float(v0[2 * p + 1])), l2e, e2);
-            if (kMasked && 2 * p + 1 >= nv) a.y = -INFINITY;
-            mxa = fmaxf(fmaxf(mxa, a.x), a.y);
-            a.x = ex2(a.x);
-            a.y = ex2(a.y);
-            s0 = __fadd2_rn(s0, a);
-            pk[p] = ptx::pack_h2_sat(a.x, a.y);
-        } else {
-            pk[p] = 0u;
-        }
-        if (!kMasked || 32 + 2 * p < nv) {
-            float2 c2;
-            if constexpr (kTable)
-                c2 = __ffma2_rn(make_float2(__uint_as_float(v1[2 * p]), __uint_as_float(v1[2 * p + 1])), l2e,
-                                __fadd2_rn(make_float2(lds_f32(er + (16 + p) * 8), lds_f32(er + (16 + p) * 8 + 4)), neg_m));
-            else
-                c2 = __ffma2_rn(make_float2(__uint_as_float(v1[2 * p]), __uint_as_float(v1[2 * p + 1])), l2e, e2);
-            if (kMasked && 32 + 2 * p + 1 >= nv) c2.y = -INFINITY;
-            mxb = fmaxf(fmaxf(mxb, c2.x), c2.y);
-            c2.x = ex2(c2.x);
-            c2.y = ex2(c2.y);
-            s1 = __fadd2_rn(s1, c2);
-            pk[16 + p] = ptx::pack_h2_sat(c2.x, c2.y);
-        } else {
-            pk[16 + p] = 0u;
-        }
-    }
-    sum = (s0.x + s0.y) + (s1.x + s1.y);
-    dmax = fmaxf(mxa, mxb);
-}
+using softmax::tile_one_pass;
+using softmax::tile_row_max;
 
 #ifdef P5_DEBUG_BUILD
 __device__ unsigned long long g_attn4_prof[32];
