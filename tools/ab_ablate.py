@@ -2,8 +2,8 @@
 
     python tools/ab_ablate.py            (P5_ATTN_CTAS=1 in the environment: one CTA per SM)
 
-impl 16 + mask: 15 = product kernel, 31 = the same with the one-pass softmax; on mask 15: +32 = no bias-table LDS (every
-tile takes the constant-bias path), +64 = no MUFU
+impl 16 + mask: 15 = product kernel, 31 = the same with the one-pass softmax; on mask 15: +64 = no bias-table LDS (every
+tile takes the constant-bias path), +128 = no MUFU
 (the exponentials become one FMUL each).  Results of the ablated variants are WRONG by construction; only the time counts.
 """
 import ctypes as C
@@ -28,7 +28,7 @@ def main():
         qkv = (rng.standard_normal((M, 3 * H * 128), dtype=np.float32) * 0.6).astype(np.float16)
         bias = (rng.standard_normal((H, 257), dtype=np.float32) * 0.5).astype(np.float32)
         flops = 4.0 * 128 * H * float(sum(t * t for t in lens))
-        for impl, what in ((31, "product (mask 15)"), (47, "one-pass softmax (mask 31)"), (16 + 15 + 32, "no table LDS"), (16 + 15 + 64, "no MUFU"), (16 + 15 + 96, "no table LDS, no MUFU"), (16 + 15 + 256, "no softmax math at all")):
+        for impl, what in ((31, "product (mask 15)"), (47, "one-pass softmax (mask 31)"), (16 + 47, "polynomial exp2 for 3/8 of the columns (mask 47)"), (16 + 15 + 64, "no table LDS"), (16 + 15 + 128, "no MUFU"), (16 + 15 + 192, "no table LDS, no MUFU"), (16 + 15 + 512, "no softmax math at all")):
             ctx = np.zeros((M, H * 128), np.float16)
             ms = C.c_float(0)
             _lib.check(lib.p5_dbg_attention(0, impl, qkv.ctypes.data, cu.ctypes.data, len(cu) - 1, H, 128, bias.ctypes.data,

@@ -31,7 +31,7 @@ def main():
         out = (C.c_uint64 * 32)()
         k4 = bool(os.environ.get("P5_KERNEL4"))
         _lib.check(lib.p5_dbg_attention_profile(0, out, 3 if k4 else 1))
-        _lib.check(lib.p5_dbg_attention(0, 5 if k4 else 16 + (31 if os.environ.get("P5_ONEPASS") else 15) + 128 + (256 if os.environ.get("P5_NOMATH") else 0), qkv.ctypes.data, cu.ctypes.data, len(cu) - 1, H, 128, bias.ctypes.data,
+        _lib.check(lib.p5_dbg_attention(0, 8 if k4 else 16 + (31 if os.environ.get("P5_ONEPASS") else 15) + (32 if os.environ.get("P5_POLY") else 0) + 256 + (512 if os.environ.get("P5_NOMATH") else 0), qkv.ctypes.data, cu.ctypes.data, len(cu) - 1, H, 128, bias.ctypes.data,
                                         ctx.ctypes.data, 0, C.byref(ms)))
         _lib.check(lib.p5_dbg_attention_profile(0, out, 3 if k4 else 1))
         v = [int(x) for x in out]

@@ -137,9 +137,10 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         attention_tc2_init_device();
         attention_tc3_init_device();
         attention_tc4_init_device();
+        attention_tc5_init_device();
         // impl 2 = second-generation tcgen05 kernel (two softmax warpgroups per item); impl 16 + f = tcgen05 kernel with feature mask f (attention_tc.cu), for A/B tests of the pipelining features
-        P5_REQUIRE((impl >= 0 && impl <= 5) || (impl >= 16 && impl < 16 + 512), P5_ERR_ARG,
-                   "impl must be 0 (mma.sync), 1 (tcgen05), 2 (tcgen05, two softmax warpgroups), 3 (tcgen05, packed-pair math) "
+        P5_REQUIRE((impl >= 0 && impl <= 5) || impl == 8 || (impl >= 16 && impl < 16 + 1024), P5_ERR_ARG,
+                   "impl must be 0 (mma.sync), 1 (tcgen05), 2 (two softmax warpgroups), 3 (packed-pair math), 4 (query-tile pairs; 8 = with phase counters), 5 (128-key tiles) "
                    "or 16..31 (first tcgen05 kernel with an explicit feature mask)");
         const int features = impl >= 16 ? impl - 16 : -1;
         cudaDeviceProp prop;
@@ -148,7 +149,7 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         const size_t inner = size_t(n_head) * kHeadDim;
         std::vector<int2> work;   // mma.sync kernel: (seq, q0)
         std::vector<int4> work4;  // tcgen05 kernel: (tok0, T, q0, 0)
-        std::vector<int4> work8;  // tcgen05 kernel 4: (tok0, T, first row of the 256-row pair, 0); impl 5 = with phase counters
+        std::vector<int4> work8;  // tcgen05 kernel 4: (tok0, T, first row of the 256-row pair, 0); impl 8 = with phase counters
         for (uint32_t s = 0; s < n_seq; ++s) {
             const int T = cu_host[s + 1] - cu_host[s];
             P5_REQUIRE(T >= 1, P5_ERR_ARG, "empty sequence %u", s);
@@ -181,10 +182,16 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         cudaStream_t st;
         P5_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         auto run = [&] {
-            if (impl == 4 || impl == 5) {
+            if (impl == 4 || impl == 8) {
                 launch_attention_tc4(st, prop.multiProcessorCount, tm_q, tm_kv, static_cast<__half*>(ctx.p),
                                      static_cast<const int4*>(wk8.p), uint32_t(work8.size()),
-                                     static_cast<const float*>(e_ext.p), n_head, max_dist, impl == 5);
+                                     static_cast<const float*>(e_ext.p), n_head, max_dist, impl == 8);
+                return;
+            }
+            if (impl == 5) {
+                launch_attention_tc5(st, prop.multiProcessorCount, tm_q, static_cast<__half*>(ctx.p),
+                                     static_cast<const int4*>(wk4.p), uint32_t(work4.size()),
+                                     static_cast<const float*>(e_ext.p), n_head, max_dist);
                 return;
             }
             if (impl == 3) {

@@ -61,16 +61,16 @@ constexpr uint32_t kSmemStage = (kSmemE + 2 * kEPad * 4 + 511) / 512 * 512;  // 
 constexpr uint32_t kStageBytes = 32 * 64;                                     // 32 rows x 32 fp16 columns
 constexpr uint32_t kSmemBar = kSmemStage + 4 * kStageBytes;
 constexpr uint32_t kNumBars = 22;
-constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatBars = 8, kFeatOnePass = 16;
-// timing-only ablations (debug library; WRONG results): 32 = every tile takes the constant-bias path (no LDS of the
-// table), 64 = the exponentials are replaced by one FMUL each (no MUFU)
-constexpr uint32_t kAblNoTable = 32, kAblNoEx2 = 64;
-// 128 = phase cycle counters of the softmax warps (debug library): clock() deltas summed over all valid warps into
+constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatBars = 8, kFeatOnePass = 16, kFeatPoly = 32;
+// timing-only ablations (debug library; WRONG results): 64 = every tile takes the constant-bias path (no LDS of the
+// table), 128 = the exponentials are replaced by one FMUL each (no MUFU)
+constexpr uint32_t kAblNoTable = 64, kAblNoEx2 = 128;
+// 256 = phase cycle counters of the softmax warps (debug library): clock() deltas summed over all valid warps into
 // g_attn_prof: 0 wait S, 1 tcgen05.ld, 2 bias, 3 max + vote (+ rescale), 4 exp/sum/pack, 5 tcgen05.st + arrive,
 // 6 epilogue wait for P.V, 7 epilogue rest, 8 between items, 9 total, 10 warp-tiles, 11 warp-items
-constexpr uint32_t kDbgProf = 128;
-// 256 = timing-only: no softmax at all (P = 0 stored right after S arrives): the rate of the TMA/MMA pipeline alone
-constexpr uint32_t kAblNoMath = 256;
+constexpr uint32_t kDbgProf = 256;
+// 512 = timing-only: no softmax at all (P = 0 stored right after S arrives): the rate of the TMA/MMA pipeline alone
+constexpr uint32_t kAblNoMath = 512;
 #ifdef P5_DEBUG_BUILD
 __device__ unsigned long long g_attn_prof[16];
 #endif
@@ -125,7 +125,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     const int4* __restrict__ work, uint32_t n_work, uint32_t n_items, uint32_t H,
                     const float* __restrict__ e_ext) {
     constexpr bool kTable = (kF & kFeatTable) != 0, kDefer = (kF & kFeatDefer) != 0, kStore = (kF & kFeatStore) != 0,
-                   kBars = (kF & kFeatBars) != 0, kOnePass = (kF & kFeatOnePass) != 0;
+                   kBars = (kF & kFeatBars) != 0, kOnePass = (kF & kFeatOnePass) != 0, kPoly = (kF & kFeatPoly) != 0;
     constexpr bool kNoTable = (kF & kAblNoTable) != 0, kNoEx2 = (kF & kAblNoEx2) != 0, kProf = (kF & kDbgProf) != 0, kNoMath = (kF & kAblNoMath) != 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -489,6 +489,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 }
                 tick(3);
                 float sa = 0.f, sb = 0.f, sc = 0.f, sd = 0.f;
+                if constexpr (kPoly) {
+                    // 3 of every 8 column pairs take their exponentials on the FMA pipe (attention_softmax.cuh)
+                    const float2 neg_m = make_float2(-m, -m);
+                    float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < 32; q += 2) {
+                        float2 a = __fadd2_rn(make_float2(z[2 * q], z[2 * q + 1]), neg_m);
+                        float2 c2 = __fadd2_rn(make_float2(z[2 * q + 2], z[2 * q + 3]), neg_m);
+                        if (softmax::poly_pair(q)) a = softmax::ex2_poly2(a);
+                        else { a.x = ex2(a.x); a.y = ex2(a.y); }
+                        if (softmax::poly_pair(q + 1)) c2 = softmax::ex2_poly2(c2);
+                        else { c2.x = ex2(c2.x); c2.y = ex2(c2.y); }
+                        s0 = __fadd2_rn(s0, a);
+                        s1 = __fadd2_rn(s1, c2);
+                        pk[q] = pack_h2(a.x, a.y);
+                        pk[q + 1] = pack_h2(c2.x, c2.y);
+                    }
+                    sa = s0.x; sb = s0.y; sc = s1.x; sd = s1.y;
+                } else {
 #pragma unroll
                 for (int c = 0; c < 32; c += 2) {
                     float p0, p1, p2, p3;
@@ -502,6 +521,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     sa += p0; sb += p1; sc += p2; sd += p3;
                     pk[c] = pack_h2(p0, p1);
                     pk[c + 1] = pack_h2(p2, p3);
+                }
                 }
                 l += (sa + sb) + (sc + sd);
                 tick(4);
@@ -572,11 +592,13 @@ AttnKernel attn_kernel(uint32_t feat) {
         case 14: return attention_tc_kernel<14>;
         case 15 + 32: return attention_tc_kernel<15 + 32>;
         case 15 + 64: return attention_tc_kernel<15 + 64>;
-        case 15 + 96: return attention_tc_kernel<15 + 96>;
         case 15 + 128: return attention_tc_kernel<15 + 128>;
-        case 31 + 128: return attention_tc_kernel<31 + 128>;
+        case 15 + 192: return attention_tc_kernel<15 + 192>;
         case 15 + 256: return attention_tc_kernel<15 + 256>;
-        case 15 + 384: return attention_tc_kernel<15 + 384>;
+        case 31 + 256: return attention_tc_kernel<31 + 256>;
+        case 47 + 256: return attention_tc_kernel<47 + 256>;
+        case 15 + 512: return attention_tc_kernel<15 + 512>;
+        case 15 + 768: return attention_tc_kernel<15 + 768>;
 #endif
         default: throw Error(P5_ERR_ARG, strf("attention feature mask %u is not built", feat));
     }
@@ -585,7 +607,7 @@ AttnKernel attn_kernel(uint32_t feat) {
 
 void attention_tc_init_device() {
 #ifdef P5_DEBUG_BUILD
-    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u, 31u, 47u, 79u, 111u, 143u, 159u, 271u, 399u})
+    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u, 31u, 47u, 79u, 143u, 207u, 271u, 287u, 303u, 527u, 783u})
 #else
     for (uint32_t f : {15u})
 #endif

@@ -66,6 +66,13 @@ void launch_attention_tc4(cudaStream_t st, int num_sms, const CUtensorMap& tm_q,
                           const int4* work256, uint32_t n_work, const float* e_ext, uint32_t H, uint32_t max_dist,
                           bool profile = false);
 
+// Fifth tcgen05 kernel (attention_tc5.cu): the first kernel's shape (two CTAs per SM, one 128-row query tile per item,
+// work128 / e_ext as there) with 128-key tiles through one S/P buffer and a chunked one-pass softmax; tm_q only (K and V
+// tiles are 128-row boxes too).
+void attention_tc5_init_device();
+void launch_attention_tc5(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, __half* ctx, const int4* work128,
+                          uint32_t n_work, const float* e_ext, uint32_t H, uint32_t max_dist);
+
 constexpr uint32_t kAttnBlockM = 64;  // query rows per attention work item
 constexpr uint32_t kHeadChunk = 64;   // residues per head work item
 constexpr uint32_t kHeadDim = 128;    // the attention kernel is specialised on ProstT5's d_kv

@@ -3,6 +3,7 @@
 // kernels need is spelled out here once.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
