@@ -74,7 +74,7 @@ def test_gemm_is_deterministic():
 
 def _impls(default):
     """Attention implementations under test: 0 = mma.sync, 1 = first tcgen05 kernel, 16 + f = the same with feature mask f,
-    2 = two softmax warpgroups per item, 3 = packed-pair math, 4 = query-tile pairs on one K/V stream (attention_tc4.cu), 5 = 128-key tiles (attention_tc5.cu).  P5_TEST_ATTN_IMPLS="3" restricts
+    2 = two softmax warpgroups per item, 3 = packed-pair math, 4 = query-tile pairs on one K/V stream (attention_tc4.cu), 5 = 128-key tiles (attention_tc5.cu), 6 = eight softmax warps per CTA (attention_tc6.cu).  P5_TEST_ATTN_IMPLS="3" restricts
     a run to some of them (kernel iteration on the GPU box)."""
     env = os.environ.get("P5_TEST_ATTN_IMPLS")
     return [int(x) for x in env.split(",")] if env else default
@@ -98,7 +98,7 @@ def _attention_ref(qkv, cu, H, bias, md):
     return out
 
 
-@pytest.mark.parametrize("impl", _impls([5, 4, 3, 2, 1, 16, 0]))
+@pytest.mark.parametrize("impl", _impls([6, 5, 4, 3, 2, 1, 16, 0]))
 @pytest.mark.parametrize("lens,H", [([1], 1), ([3], 1), ([64], 2), ([65, 1, 130], 2), ([352, 352], 4),
                                     ([700, 66, 1026], 2), ([2500], 1), ([128, 129, 127, 256, 257], 3),
                                     ([16, 17, 33, 48, 49, 80, 81, 96, 97, 112, 113, 4002], 2)])
@@ -127,7 +127,7 @@ def _many_lens(seed, n, lo, hi):
 # item-spanning MMA stream, 4 = TMA-store epilogue, 8 = one tcgen05.commit per event, 16 = one-pass softmax); the debug
 # library builds the masks 0, 1, 2, 4, 7, 8, 15 (the default = impl 1) and 31.  Far more work items than resident CTAs (2 x 148), several
 # heads per CTA, ragged tails: every item-boundary path of the persistent kernel is taken many times.
-@pytest.mark.parametrize("impl", _impls([5, 4, 3, 2, 1, 16, 17, 18, 20, 23, 24, 31, 47, 0]))
+@pytest.mark.parametrize("impl", _impls([6, 5, 4, 3, 2, 1, 16, 17, 18, 20, 23, 24, 31, 47, 63, 0]))
 @pytest.mark.parametrize("lens,H", [(_many_lens(1, 90, 3, 420), 5), (_many_lens(2, 400, 3, 70), 3),
                                     ([352] * 40, 8), (_many_lens(3, 12, 900, 1500), 4)])
 def test_attention_many_items(lens, H, impl):
@@ -197,7 +197,7 @@ def test_attention_table_ring_wraps_bit_identical():
     assert np.abs(outs[0].astype(np.float32) - _attention_ref(qkv, cu, H, bias, md)).max() < 6e-3
 
 
-@pytest.mark.parametrize("impl", _impls([5, 4, 3, 2, 1, 0]))
+@pytest.mark.parametrize("impl", _impls([6, 5, 4, 3, 2, 1, 0]))
 def test_attention_peaked_scores(impl):
     """Un-scaled T5 scores can be large: one dominant key per row must not overflow or lose the row."""
     lib = _lib.load_debug()
@@ -215,7 +215,7 @@ def test_attention_peaked_scores(impl):
     assert np.abs(ctx.astype(np.float32) - ref).max() < 2e-2
 
 
-@pytest.mark.parametrize("impl", _impls([5, 4, 3, 2, 1, 16, 0]))
+@pytest.mark.parametrize("impl", _impls([6, 5, 4, 3, 2, 1, 16, 0]))
 def test_attention_peaked_scores_many_items(impl):
     """Accumulator rescales (large un-scaled scores) while items are pipelined back to back in each CTA."""
     lib = _lib.load_debug()
@@ -235,7 +235,7 @@ def test_attention_peaked_scores_many_items(impl):
     assert np.abs(ctx.astype(np.float32) - ref).max() < 2e-2
 
 
-@pytest.mark.parametrize("impl", _impls([5, 4, 3, 2, 1, 16, 0]))
+@pytest.mark.parametrize("impl", _impls([6, 5, 4, 3, 2, 1, 16, 0]))
 def test_attention_is_independent_of_the_neighbour_sequence(impl):
     """Packed layout: the query rows past a sequence's end are the next sequence's tokens.  They must not leak into the
     sequence's own rows - not even through the warp-wide vote that triggers an accumulator rescale (peaked scores make

@@ -5,7 +5,7 @@
 Shapes: config 2 (256 x 352 tokens x 32 heads), a config-4-like ragged mix and a config-5-like long mix.
 impl 16 + f runs feature mask f (1 = TMA-fetched bias table, 2 = deferred epilogue + item-spanning MMA stream,
 4 = TMA-store epilogue, 8 = one tcgen05.commit per event, 16 = one-pass softmax; 31 = mask 15, 47 = mask 31, 63 = mask 47 = mask 15 + 32: polynomial exp2 for 3/8 of the columns); impl 4 is the
-fourth kernel (query-tile pairs on one K/V ring, attention_tc4.cu), impl 5 the fifth (128-key tiles, attention_tc5.cu), impl 2 is the second-generation kernel (two softmax
+fourth kernel (query-tile pairs on one K/V ring, attention_tc4.cu), impl 5 the fifth (128-key tiles, attention_tc5.cu), impl 6 the sixth (eight softmax warps per CTA, attention_tc6.cu), impl 2 is the second-generation kernel (two softmax
 warpgroups per item, attention_tc2.cu); impl 0 is the mma.sync kernel.  Every variant is also compared bit for bit with mask 0.
 """
 import argparse
@@ -56,12 +56,12 @@ def main():
         flops = 4.0 * 128 * H * float(sum(t * t for t in lens))
         base = None
         row = {}
-        for impl in (16, 31, 47, 63, 5, 4, 2, 3, 0):
+        for impl in (16, 31, 47, 63, 6, 5, 4, 2, 3, 0):
             ctx, ms = run(lib, impl, qkv, cu, H, bias, a.iters)
             if base is None:
                 base = ctx
             same = bool(np.array_equal(ctx.view(np.uint16), base.view(np.uint16))) if impl in (16, 31) else None
-            if impl in (2, 3, 4, 5, 47, 63):  # different summation order of the row sums: compare within fp16 noise
+            if impl in (2, 3, 4, 5, 6, 47, 63):  # different summation order of the row sums: compare within fp16 noise
                 row["impl%d_maxdiff_vs_mask0" % impl] = float(np.abs(ctx.astype(np.float32) - base.astype(np.float32)).max())
             row["impl%d" % impl] = {"ms": ms, "tflops": flops / ms * 1e-9, "bit_identical_to_mask0": same}
             print("%-34s impl %2d  %.3f ms  %6.1f TFLOP/s  same=%s" % (name, impl, ms, flops / ms * 1e-9, same), flush=True)

@@ -96,8 +96,8 @@ extern "C" int p5_set_option(p5_model* h, const char* key, int64_t value) {
             }
         } else if (k == "attn_impl") {
 #ifdef P5_DEBUG_BUILD
-            P5_REQUIRE(value >= 0 && value <= 5, P5_ERR_ARG,
-                       "attn_impl must be 0 (mma.sync), 1 (tcgen05, the product kernel), 2 (tcgen05, two softmax warpgroups), 3 (tcgen05, packed-pair math), 4 (tcgen05, query-tile pairs) or 5 (tcgen05, 128-key tiles)");
+            P5_REQUIRE(value >= 0 && value <= 6, P5_ERR_ARG,
+                       "attn_impl must be 0 (mma.sync), 1 (tcgen05, the product kernel), 2 (tcgen05, two softmax warpgroups), 3 (tcgen05, packed-pair math), 4 (tcgen05, query-tile pairs), 5 (tcgen05, 128-key tiles) or 6 (tcgen05, eight softmax warps)");
 #else
             P5_REQUIRE(value == 1, P5_ERR_ARG, "attn_impl: this library carries the tcgen05 kernel (1) only; the A/B "
                                                "implementations 0, 2, 3 are in libprostt5_b200_debug.so");

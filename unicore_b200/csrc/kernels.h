@@ -73,6 +73,12 @@ void attention_tc5_init_device();
 void launch_attention_tc5(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, __half* ctx, const int4* work128,
                           uint32_t n_work, const float* e_ext, uint32_t H, uint32_t max_dist);
 
+// Sixth tcgen05 kernel (attention_tc6.cu): the first kernel's pipeline with eight softmax warps per CTA (the two warps of
+// a TMEM lane quarter split a key tile's columns), one-pass softmax; arguments as for the first kernel, no store descriptor.
+void attention_tc6_init_device();
+void launch_attention_tc6(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, const CUtensorMap& tm_kv, __half* ctx,
+                          const int4* work128, uint32_t n_work, const float* e_ext, uint32_t H, uint32_t max_dist);
+
 constexpr uint32_t kAttnBlockM = 64;  // query rows per attention work item
 constexpr uint32_t kHeadChunk = 64;   // residues per head work item
 constexpr uint32_t kHeadDim = 128;    // the attention kernel is specialised on ProstT5's d_kv

@@ -361,6 +361,7 @@ void DeviceCtx::init(int device, const Model* m) {
     attention_tc3_init_device();
     attention_tc4_init_device();
     attention_tc5_init_device();
+    attention_tc6_init_device();
 #endif
 }
 
@@ -604,7 +605,9 @@ void DeviceCtx::forward(const MetaLayout& l, const int32_t* meta_d, uint8_t* let
         gemm(Epi::StoreF16, tm_xn, L.tm_qkv, qkv.p, 3 * inner, d);
         prof_begin(PC_ATTN);
 #ifdef P5_DEBUG_BUILD
-        if (opt.attn_impl == 5 && e_ext)
+        if (opt.attn_impl == 6 && e_ext)
+            launch_attention_tc6(stream, num_sms, tm_q, tm_kv, ctx.as<__half>(), aw128, l.n_aw128, e_ext, hp.n_head, hp.max_distance);
+        else if (opt.attn_impl == 5 && e_ext)
             launch_attention_tc5(stream, num_sms, tm_q, ctx.as<__half>(), aw128, l.n_aw128, e_ext, hp.n_head, hp.max_distance);
         else if (opt.attn_impl == 4 && e_ext)
             launch_attention_tc4(stream, num_sms, tm_q, tm_kv, ctx.as<__half>(), aw256, l.n_aw256, e_ext, hp.n_head, hp.max_distance);
