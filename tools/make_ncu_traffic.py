@@ -9,6 +9,7 @@ import csv
 import datetime
 import json
 import os
+import re
 import subprocess
 import sys
 
@@ -45,13 +46,16 @@ def main():
     assert len(launches) == 4, [l["name"] for l in launches]
     # identify the shapes: epilogue template argument, and of the two residual GEMMs the shorter one is O
     by = {}
-    adds = sorted([l for l in launches if "(p5::Epi)2" in l["name"]], key=lambda l: l["ms"])
+    def epi(l):  # epilogue template argument: "...(p5::Epi)2>" or "<2, 256, 6, 2>" depending on the ncu version
+        m = re.search(r"\(p5::Epi\)(\d+)", l["name"]) or re.search(r"<\s*\d+,\s*\d+,\s*\d+,\s*(\d+)\s*>", l["name"])
+        return int(m.group(1)) if m else -1
+    adds = sorted([l for l in launches if epi(l) in (2, 5)], key=lambda l: l["ms"])
     by["o"], by["ffn_out"] = adds[0], adds[1]
-    by["qkv"] = next(l for l in launches if "(p5::Epi)0" in l["name"])
-    by["ffn_in"] = next(l for l in launches if "(p5::Epi)1" in l["name"])
+    by["qkv"] = next(l for l in launches if epi(l) == 0)
+    by["ffn_in"] = next(l for l in launches if epi(l) == 1)
     per = {}
     for k, (N, K, osz) in SHAPES.items():
-        alg = M * K * 2 + N * K * 2 + M * N * osz
+        alg = M * K * 2 + N * K * 2 + M * N * osz * (2 if osz == 4 else 1)  # the fp32 residual is read and written
         l = by[k]
         per[f"{k} [{M}x{K}]x[{N}x{K}]^T"] = {"read": l["read"], "write": l["write"], "ms": round(l["ms"], 4), "tensor_pipe_pct": round(l["tensor_pipe_pct"], 1),
                                                "algorithmic_bytes": alg, "traffic_over_algorithmic": round((l["read"] + l["write"]) / alg, 3),

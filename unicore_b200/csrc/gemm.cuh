@@ -12,6 +12,7 @@
 // kCtaGroup == 2 pairs two SMs on one 256 x kBlockN tile (cta_group::2): each CTA loads its own 128
 // rows of A and HALF of the B tile, halving B traffic per SM.
 #pragma once
+#include "norm.cuh"
 #include "ptx.cuh"
 
 namespace p5 {
@@ -23,6 +24,18 @@ enum class Epi : int {
     StoreF32 = 3,      // C(fp32) = acc                   (conv-head taps, p10)
     GatedGeluF16 = 4,  // C[:, i] = fp16(gelu_new(acc[:, 2i]) * acc[:, 2i+1]): gate/up rows interleaved in B
                        // (gated T5 v1.1 FFN, p8 variant); C has N/2 columns
+    AddF32Norm = 5,    // AddF32 with N == the row width of C, plus the RMSNorm that follows the residual add (p7/p8 -> p3):
+                       // the CTA whose N tile is the LAST of a 128-row block to land normalises that block from L2
+                       // (xn = fp16(C * rsqrt(mean(C^2) + eps) * w), norm.cuh: the stand-alone kernel's per-row code)
+};
+
+// Epi::AddF32Norm only: where the fused RMSNorm reads its weight and writes its output.  counters[row / 128] counts the N
+// tiles of a 128-row block that have landed; the last arriver resets it, so the array is all zero between launches.
+struct NormFuse {
+    const float* w = nullptr;
+    __half* xn = nullptr;
+    uint32_t* counters = nullptr;
+    float eps = 0.f;
 };
 
 __device__ __forceinline__ float gelu_new(float x) {  // HF "gelu_new" (tanh approximation)
@@ -35,6 +48,7 @@ struct GemmShape {
     uint32_t band_m;  // m-tiles per L2 band of the tile order
     uint32_t idesc_extra;  // debug library only: OR-ed into the instruction descriptor (bf16 operand formats); bit 31 =
                            // skip the epilogue stores.  Always 0 in the product library.
+    NormFuse norm;         // Epi::AddF32Norm
 };
 
 // The "skip the epilogue stores" timing experiment exists in the debug library only: in the product build the test is
@@ -63,7 +77,7 @@ struct GemmSmem {
     static constexpr uint32_t kStagingOffset = kStages * kStageBytes;
     static constexpr uint32_t kStagingBytes = 4 * 2 * 4096;
     static constexpr uint32_t kBarOffset = kStagingOffset + kStagingBytes;
-    // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem ptr
+    // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem ptr, fused-norm flag
     static constexpr uint32_t kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16;
     static constexpr uint32_t kDynamic = kTotal + 1024;  // slack for manual 1024 B alignment
 };
@@ -99,6 +113,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint64_t* tmem_full_bar = empty_bar + kStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    volatile uint32_t* norm_flag = tmem_ptr_smem + 1;  // Epi::AddF32Norm: "this CTA normalises the block"
 
     const uint32_t warp_idx = threadIdx.x >> 5;  // warp-uniform
     const uint32_t lane = ptx::lane_id();
@@ -296,13 +311,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         ptx::fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            if constexpr (kEpi == Epi::AddF32)
+                            if constexpr (kEpi == Epi::AddF32 || kEpi == Epi::AddF32Norm)
                                 ptx::tma_reduce_add_2d(&tma_c, stage_base + sbuf * 4096, int32_t(col0), int32_t(row0));
                             else
                                 ptx::tma_store_2d(&tma_c, stage_base + sbuf * 4096, int32_t(col0), int32_t(row0));
                             ptx::bulk_commit();
                         }
                         sbuf ^= 1;
+                    }
+                }
+                if constexpr (kEpi == Epi::AddF32Norm) {
+                    // This CTA's 128 rows x kBlockN columns of C += acc are on their way.  Count the tile in; the CTA
+                    // that brings the block's LAST N tile normalises the 128 rows (they are in L2: the other N tiles of
+                    // a row tile are computed at the same time by neighbouring pairs).
+                    if (lane == 0) ptx::bulk_wait<0>();  // this warp's reduce-adds have been performed
+                    __syncwarp();
+                    __threadfence();
+                    ptx::named_bar_sync(1, 128);  // the four epilogue warps
+                    const uint32_t blk = mt * kCtaGroup + cta_rank;
+                    if (ew == 0 && lane == 0) {
+                        const uint32_t old = atomicAdd(&s.norm.counters[blk], 1u);
+                        const bool last = old + 1 == num_nt;
+                        if (last) s.norm.counters[blk] = 0;  // zero again for the next launch
+                        *norm_flag = last ? 1u : 0u;
+                    }
+                    ptx::named_bar_sync(1, 128);
+                    if (*norm_flag != 0u) {
+                        __threadfence();
+                        const uint32_t r_first = blk * kGemmBlockM + ew * 32;
+#pragma unroll 1
+                        for (uint32_t rr = 0; rr < 32; ++rr) {
+                            const uint32_t rw = r_first + rr;
+                            if (rw < s.M)
+                                norm::rmsnorm_row<true>(reinterpret_cast<const float*>(Cptr) + size_t(rw) * s.ldc, s.norm.w, s.norm.eps,
+                                                        s.norm.xn + size_t(rw) * s.ldc, nullptr, s.N, lane);
+                        }
                     }
                 }
             }

@@ -4,6 +4,7 @@
 #include "kernels.h"
 
 #include "common.h"
+#include "norm.cuh"
 
 namespace p5 {
 
@@ -35,47 +36,39 @@ rmsnorm_kernel(const int32_t* __restrict__ ids, const __half* __restrict__ embd,
     const uint32_t row = blockIdx.x * kNormWarps + (threadIdx.x >> 5);
     const uint32_t lane = threadIdx.x & 31;
     if (row >= M) return;
+    if constexpr (!kEmbed) {
+        // (the same per-row code the residual-add GEMM epilogue runs when it normalises a finished block: norm.cuh)
+        norm::rmsnorm_row<false>(h_in + size_t(row) * d, w, eps, xn + size_t(row) * d,
+                                 out_f32 ? out_f32 + size_t(row) * d : nullptr, d, lane);
+        return;
+    }
     constexpr int kMaxIter = 8;
     float4 v[kMaxIter];
     const uint32_t n4 = d >> 2;
     float ss = 0.f;
-    const __half* erow = nullptr;
-    if constexpr (kEmbed) {
-        int32_t id = ids[row];
-        if (id < 0 || id >= (int32_t)n_vocab) id = 0;
-        erow = embd + size_t(id) * d;
-    }
-    const float4* hrow = reinterpret_cast<const float4*>(h_in + size_t(row) * d);
+    int32_t id = ids[row];
+    if (id < 0 || id >= (int32_t)n_vocab) id = 0;
+    const __half* erow = embd + size_t(id) * d;
 #pragma unroll
     for (int it = 0; it < kMaxIter; ++it) {
         const uint32_t c = it * 32 + lane;
         if (c < n4) {
-            float4 x;
-            if constexpr (kEmbed) {
-                const uint2 u = *reinterpret_cast<const uint2*>(erow + c * 4);
-                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-                x = make_float4(a.x, a.y, b.x, b.y);
-                reinterpret_cast<float4*>(h_out + size_t(row) * d)[c] = x;
-            } else {
-                x = hrow[c];
-            }
+            const uint2 u = *reinterpret_cast<const uint2*>(erow + c * 4);
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+            const float4 x = make_float4(a.x, a.y, b.x, b.y);
+            reinterpret_cast<float4*>(h_out + size_t(row) * d)[c] = x;
             v[it] = x;
             ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
         }
     }
     // rows wider than kMaxIter*128 (not ProstT5): accumulate the remainder straight from memory
     for (uint32_t c = kMaxIter * 32 + lane; c < n4; c += 32) {
-        float4 x;
-        if constexpr (kEmbed) {
-            const uint2 u = *reinterpret_cast<const uint2*>(erow + c * 4);
-            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-            x = make_float4(a.x, a.y, b.x, b.y);
-            reinterpret_cast<float4*>(h_out + size_t(row) * d)[c] = x;
-        } else {
-            x = hrow[c];
-        }
+        const uint2 u = *reinterpret_cast<const uint2*>(erow + c * 4);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        const float4 x = make_float4(a.x, a.y, b.x, b.y);
+        reinterpret_cast<float4*>(h_out + size_t(row) * d)[c] = x;
         ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
     }
     ss = warp_sum(ss);
@@ -95,7 +88,7 @@ rmsnorm_kernel(const int32_t* __restrict__ ids, const __half* __restrict__ embd,
     }
     for (uint32_t c = kMaxIter * 32 + lane; c < n4; c += 32) {
         const float4 g = w4[c];
-        const float4 x = kEmbed ? reinterpret_cast<const float4*>(h_out + size_t(row) * d)[c] : hrow[c];
+        const float4 x = reinterpret_cast<const float4*>(h_out + size_t(row) * d)[c];
         const float4 y = make_float4(x.x * r * g.x, x.y * r * g.y, x.z * r * g.z, x.w * r * g.w);
         store_half4(xrow + c * 4, y.x, y.y, y.z, y.w);
         if (out_f32) reinterpret_cast<float4*>(out_f32 + size_t(row) * d)[c] = y;
