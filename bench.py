@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-4 / config-5 steps")
     ap.add_argument("--cpu-sample-seqs", type=int, default=6)
+    ap.add_argument("--fuse-norm", action="store_true", help="A/B only: RMSNorm inside the residual-add GEMM epilogues (option fuse_norm = 1)")
     ap.add_argument("--attn-impl", type=int, default=-1,
                     help="A/B only: run on libprostt5_b200_debug.so with its option attn_impl (0, 2, 3); never used by the driver")
     args = ap.parse_args()
@@ -294,6 +295,8 @@ def main():
     pred.set_option("profile", 1)
     if args.attn_impl >= 0:
         pred.set_option("attn_impl", args.attn_impl)
+    if args.fuse_norm:
+        pred.set_option("fuse_norm", 1)
     pred.stage(aa, off)
     for _ in range(args.warmup):
         pred.run_staged(None)

@@ -75,6 +75,9 @@ int p5_bias_table(const p5_model* m, uint32_t head, float* out);
  *                       libprostt5_b200_debug.so)
  *   "attn_impl"         1: the tcgen05 attention kernel (the only one in this library; the A/B implementations
  *                       0 = mma.sync, 2, 3 exist in libprostt5_b200_debug.so)
+ *   "fuse_norm"         0 (default): the RMSNorm that follows a residual add is a separate kernel; 1: it runs inside that
+ *                       GEMM's epilogue (one of the CTAs that land the N tiles of a 128-row block normalises it from L2).
+ *                       Same per-row code, bit-identical results; measured slower (profiles/r02/README.md), kept for A/B
  *   "profile"           1: time every kernel class with CUDA events on the launch stream (p5_get_stats) */
 int p5_set_option(p5_model* m, const char* key, int64_t value);
 

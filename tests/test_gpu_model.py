@@ -169,6 +169,27 @@ def test_gemm_variants_agree(tiny, tiny_dir):
         assert dbg.predict(seqs) == a
 
 
+def test_fused_norm_is_bit_identical(tiny, tiny_oracle):
+    """Option `fuse_norm = 1`: the RMSNorm behind a residual add runs in that GEMM's epilogue (one of the CTAs that land the N
+    tiles of a 128-row block normalises it from L2) instead of the stand-alone kernel: same per-row code, same bits -
+    letters AND hidden states, several batches, ragged lengths."""
+    rng = np.random.default_rng(31)
+    seqs = [random_protein(rng, int(L)) for L in rng.integers(1, 400, 60)]
+    tiny.set_option("max_batch_tokens", 3000)
+    try:
+        a = tiny.predict(seqs)
+        ha = tiny.encode_debug(seqs[3])
+        tiny.set_option("fuse_norm", 1)
+        b = tiny.predict(seqs)
+        hb = tiny.encode_debug(seqs[3])
+    finally:
+        tiny.set_option("fuse_norm", 0)
+        tiny.set_option("max_batch_tokens", 92160)
+    assert a == b
+    for x, y in zip(ha, hb):
+        np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
+
+
 def test_split_len(tiny):
     rng = np.random.default_rng(14)
     s = random_protein(rng, 700)
@@ -279,6 +300,18 @@ def test_config5_long_sequence_matches_the_oracle_fixture(full):
     lo = max(0, i - 2)
     batch = [aa[int(off[k]):int(off[k + 1])].tobytes() for k in range(lo, lo + 5)]
     assert full.predict(batch, split_len=0)[i - lo] == got.tobytes()
+
+
+def test_fused_norm_is_bit_identical_at_full_size(full):
+    """The same at ProstT5's shapes (N = 1024: four N tiles per 128-row block, 8-CTA clusters, the rotating normaliser)."""
+    aa, off = spec.synthetic_proteome("config2", n=64)
+    a = full.predict_packed(aa, off)
+    full.set_option("fuse_norm", 1)
+    try:
+        b = full.predict_packed(aa, off)
+    finally:
+        full.set_option("fuse_norm", 0)
+    np.testing.assert_array_equal(a, b)
 
 
 def test_config2_properties(full):

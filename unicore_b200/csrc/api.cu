@@ -106,6 +106,8 @@ extern "C" int p5_set_option(p5_model* h, const char* key, int64_t value) {
         } else if (k == "map_rare_to_x") {
             o.map_rare_to_x = value != 0;
             model_rebuild_token_table(*h->m);
+        } else if (k == "fuse_norm") {
+            o.fuse_norm = value != 0;
         } else if (k == "profile") {
             o.profile = value != 0;
         } else {

@@ -227,6 +227,69 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         uint32_t sbuf = 0;
         uint32_t accum_iter = 0;
         constexpr bool kF16Out = (kEpi == Epi::StoreF16 || kEpi == Epi::StoreF16Relu);
+        // Epi::AddF32Norm: a finished tile (128 rows x kBlockN columns of C += acc) is counted into its 128-row block; the
+        // CTA that brings the block's LAST N tile normalises the 128 rows (they are in L2: the other N tiles of a row tile
+        // are computed at the same time by neighbouring pairs).  `newer` = bulk groups issued after that tile's.
+        [[maybe_unused]] bool have_pending = false;
+        [[maybe_unused]] uint32_t pending_blk = 0;
+        // Who normalises: with the N tiles of a row tile on num_nt neighbouring pairs in the same round (num_clusters a
+        // multiple of num_nt: the product's launch geometry) the job ROTATES - N tile (mt mod num_nt) waits for the other
+        // arrivals of its block - because "the last arriver does it" feeds on itself: the CTA that normalised once is late for
+        // its next tile, arrives last again, and ends up doing every block of its row tiles (measured: +330 us per launch).
+        // The waits form no cycle: a CTA counts its tiles in in order and only ever waits for EARLIER-or-equal tiles of
+        // CTAs that are resident (persistent grid).  Other geometries keep the wait-free last-arriver rule.
+        [[maybe_unused]] const bool norm_rotate = (num_clusters % num_nt) == 0;
+        [[maybe_unused]] uint32_t pending_mt = 0, pending_nt = 0;
+        [[maybe_unused]] auto norm_count_in = [&](uint32_t blk, uint32_t newer) {
+            if (lane == 0) {  // that tile's reduce-adds have been performed
+                if (newer == 0) ptx::bulk_wait<0>();
+                else ptx::bulk_wait<kBlockN / 32>();
+            }
+            __syncwarp();
+            __threadfence();
+            ptx::named_bar_sync(1, 128);  // the four epilogue warps
+            if (ew == 0 && lane == 0) {
+                const uint32_t old = atomicAdd(&s.norm.counters[blk], 1u);
+                bool mine;
+                if (norm_rotate) {
+                    mine = pending_nt == pending_mt % num_nt;
+                    if (mine) {
+                        volatile uint32_t* cnt = s.norm.counters + blk;
+                        while (*cnt < num_nt) __nanosleep(200);
+                    }
+                } else {
+                    mine = old + 1 == num_nt;
+                }
+                if (mine) {
+                    __threadfence();
+                    s.norm.counters[blk] = 0;  // zero again for the next launch
+                }
+                *norm_flag = mine ? 1u : 0u;
+            }
+            ptx::named_bar_sync(1, 128);
+            if (*norm_flag != 0u) {
+                __threadfence();
+                const uint32_t r_first = blk * kGemmBlockM + ew * 32;
+                const float* c_f32 = reinterpret_cast<const float*>(Cptr);
+                if (s.N <= norm::kMaxIter * 128) {  // four rows in flight per warp: the warp works alone on its 32 rows
+#pragma unroll 1
+                    for (uint32_t rr = 0; rr < 32; rr += 4) {
+                        const uint32_t rw = r_first + rr;
+                        if (rw < s.M)
+                            norm::rmsnorm_rows<true, 4>(c_f32 + size_t(rw) * s.ldc, s.ldc, int(min(4u, s.M - rw)), s.norm.w, s.norm.eps,
+                                                        s.norm.xn + size_t(rw) * s.ldc, s.N, lane);
+                    }
+                } else {
+#pragma unroll 1
+                    for (uint32_t rr = 0; rr < 32; ++rr) {
+                        const uint32_t rw = r_first + rr;
+                        if (rw < s.M)
+                            norm::rmsnorm_row<true>(c_f32 + size_t(rw) * s.ldc, s.norm.w, s.norm.eps, s.norm.xn + size_t(rw) * s.ldc,
+                                                    nullptr, s.N, lane);
+                    }
+                }
+            }
+        };
         for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++accum_iter) {
             uint32_t mt, nt;
             tile_coords(t, num_mt, num_nt, s.band_m, mt, nt);
@@ -276,6 +339,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             } else {
                 constexpr uint32_t kColsPerStore = kF16Out ? 64 : 32;  // 128 bytes per row either way
                 constexpr uint32_t kChunks = kBlockN / kColsPerStore;
+                [[maybe_unused]] uint32_t groups_this_tile = 0;
 #pragma unroll 1
                 for (uint32_t c = 0; c < kChunks; ++c) {
                     uint32_t pk[32];  // the 128 bytes of this lane's row
@@ -317,38 +381,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                 ptx::tma_store_2d(&tma_c, stage_base + sbuf * 4096, int32_t(col0), int32_t(row0));
                             ptx::bulk_commit();
                         }
+                        ++groups_this_tile;
                         sbuf ^= 1;
                     }
                 }
                 if constexpr (kEpi == Epi::AddF32Norm) {
-                    // This CTA's 128 rows x kBlockN columns of C += acc are on their way.  Count the tile in; the CTA
-                    // that brings the block's LAST N tile normalises the 128 rows (they are in L2: the other N tiles of
-                    // a row tile are computed at the same time by neighbouring pairs).
-                    if (lane == 0) ptx::bulk_wait<0>();  // this warp's reduce-adds have been performed
-                    __syncwarp();
-                    __threadfence();
-                    ptx::named_bar_sync(1, 128);  // the four epilogue warps
-                    const uint32_t blk = mt * kCtaGroup + cta_rank;
-                    if (ew == 0 && lane == 0) {
-                        const uint32_t old = atomicAdd(&s.norm.counters[blk], 1u);
-                        const bool last = old + 1 == num_nt;
-                        if (last) s.norm.counters[blk] = 0;  // zero again for the next launch
-                        *norm_flag = last ? 1u : 0u;
-                    }
-                    ptx::named_bar_sync(1, 128);
-                    if (*norm_flag != 0u) {
-                        __threadfence();
-                        const uint32_t r_first = blk * kGemmBlockM + ew * 32;
-#pragma unroll 1
-                        for (uint32_t rr = 0; rr < 32; ++rr) {
-                            const uint32_t rw = r_first + rr;
-                            if (rw < s.M)
-                                norm::rmsnorm_row<true>(reinterpret_cast<const float*>(Cptr) + size_t(rw) * s.ldc, s.norm.w, s.norm.eps,
-                                                        s.norm.xn + size_t(rw) * s.ldc, nullptr, s.N, lane);
-                        }
-                    }
+                    // This tile's reduce-adds are on their way; the PREVIOUS tile's have had a whole tile of time to be
+                    // performed: count that one in now (waiting for this tile's own completion here would put the L2
+                    // reduction latency on the epilogue's critical path, tile after tile).
+                    // (a tile cut by the end of M issues fewer groups: then wait for everything)
+                    if (have_pending) norm_count_in(pending_blk, groups_this_tile == kChunks ? kChunks : 0u);
+                    pending_blk = mt * kCtaGroup + cta_rank;
+                    pending_mt = mt;
+                    pending_nt = nt;
+                    have_pending = true;
                 }
             }
+        }
+        if constexpr (kEpi == Epi::AddF32Norm) {
+            if (have_pending) norm_count_in(pending_blk, 0);
         }
         if (lane == 0) ptx::bulk_wait<0>();  // all stores of this warp have completed before the CTA retires
     }

@@ -189,6 +189,7 @@ void launch_epi(cudaStream_t stream, int num_sms, Epi epi, const CUtensorMap& ta
         case Epi::StoreF16: launch_one<kCtaGroup, kBlockN, kStages, Epi::StoreF16>(stream, num_sms, ta, tb, C, s); break;
         case Epi::StoreF16Relu: launch_one<kCtaGroup, kBlockN, kStages, Epi::StoreF16Relu>(stream, num_sms, ta, tb, C, s); break;
         case Epi::AddF32: launch_one<kCtaGroup, kBlockN, kStages, Epi::AddF32>(stream, num_sms, ta, tb, C, s); break;
+        case Epi::AddF32Norm: launch_one<kCtaGroup, kBlockN, kStages, Epi::AddF32Norm>(stream, num_sms, ta, tb, C, s); break;
         case Epi::StoreF32: launch_one<kCtaGroup, kBlockN, kStages, Epi::StoreF32>(stream, num_sms, ta, tb, C, s); break;
         case Epi::GatedGeluF16: launch_one<kCtaGroup, kBlockN, kStages, Epi::GatedGeluF16>(stream, num_sms, ta, tb, C, s); break;
     }
@@ -202,6 +203,8 @@ void init_variant() {
     P5_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kCtaGroup, kBlockN, kStages, Epi::StoreF16Relu>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kDynamic));
     P5_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kCtaGroup, kBlockN, kStages, Epi::AddF32>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kDynamic));
+    P5_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kCtaGroup, kBlockN, kStages, Epi::AddF32Norm>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kDynamic));
     P5_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kCtaGroup, kBlockN, kStages, Epi::StoreF32>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kDynamic));
@@ -230,7 +233,9 @@ uint32_t gemm_b_box_rows(int variant) {
 }
 
 void gemm_launch(cudaStream_t stream, int num_sms, int variant, Epi epi, const CUtensorMap& tma_a,
-                 const CUtensorMap& tma_b, void* C, uint32_t ldc, uint32_t M, uint32_t N, uint32_t K) {
+                 const CUtensorMap& tma_b, void* C, uint32_t ldc, uint32_t M, uint32_t N, uint32_t K, const NormFuse* norm) {
+    P5_REQUIRE(epi != Epi::AddF32Norm || (norm && norm->w && norm->xn && norm->counters && N == ldc && N % 4 == 0), P5_ERR_ARG,
+               "fused RMSNorm needs its weight, output and counters, and the whole row (N %u, ldc %u)", N, ldc);
     P5_REQUIRE(N % 8 == 0 && K % 8 == 0, P5_ERR_ARG, "GEMM N (%u) and K (%u) must be multiples of 8", N, K);
     const bool f16_out = (epi == Epi::StoreF16 || epi == Epi::StoreF16Relu || epi == Epi::GatedGeluF16);
     P5_REQUIRE(epi != Epi::GatedGeluF16 || N % 16 == 0, P5_ERR_ARG, "gated GEMM needs N (%u) to be a multiple of 16", N);
@@ -247,7 +252,7 @@ void gemm_launch(cudaStream_t stream, int num_sms, int variant, Epi epi, const C
     // skips the epilogue stores (timing experiments).  In the product library both are compiled out (common.h).
     static const uint32_t idesc_extra = (env_flag("P5_GEMM_BF16") ? ((1u << 7) | (1u << 10)) : 0u) |
                                         (env_flag("P5_GEMM_NOSTORE") ? (1u << 31) : 0u);
-    GemmShape s{M, N, K, ldc, band, idesc_extra};
+    GemmShape s{M, N, K, ldc, band, idesc_extra, norm ? *norm : NormFuse{}};
     if (M == 0 || N == 0) return;
     switch (variant) {
 #ifdef P5_DEBUG_BUILD

@@ -215,7 +215,7 @@ public:
 
     // workspace for `cap` tokens
     uint32_t cap = 0;
-    DevBuf h, xn, qkv, ctx, ffn, taps;
+    DevBuf h, xn, qkv, ctx, ffn, taps, norm_cnt;
     CUtensorMap tm_xn, tm_ctx, tm_ffn, tm_q, tm_kv, tm_ctx_st;
 
     Slot slots[2];
@@ -538,11 +538,13 @@ void DeviceCtx::ensure_workspace(uint32_t tokens) {
     ctx.alloc(n * inner * 2);
     ffn.alloc(n * ff * 2);
     taps.alloc(n * size_t(hp.cnn_kernel) * hp.cnn_hidden * 4);
+    norm_cnt.alloc(n / 128 * 4);  // landed N tiles per 128-row block (fused RMSNorm): zero between launches
     // rows beyond a batch's M hold stale data: they only feed output rows that are never stored
     P5_CUDA(cudaMemsetAsync(qkv.p, 0, qkv.bytes, stream));  // attention tiles read (masked) K/V rows past a sequence's end
     P5_CUDA(cudaMemsetAsync(xn.p, 0, xn.bytes, stream));
     P5_CUDA(cudaMemsetAsync(ctx.p, 0, ctx.bytes, stream));
     P5_CUDA(cudaMemsetAsync(ffn.p, 0, ffn.bytes, stream));
+    P5_CUDA(cudaMemsetAsync(norm_cnt.p, 0, norm_cnt.bytes, stream));
     tm_xn = make_kmajor_tensor_map(xn.p, n, d, d, kGemmBlockM);
     tm_ctx = make_kmajor_tensor_map(ctx.p, n, inner, inner, kGemmBlockM);
     tm_ffn = make_kmajor_tensor_map(ffn.p, n, ff, ff, kGemmBlockM);
@@ -590,12 +592,26 @@ void DeviceCtx::forward(const MetaLayout& l, const int32_t* meta_d, uint8_t* let
     const int4* aw128 = reinterpret_cast<const int4*>(meta_d + l.off_aw128);
     const int4* aw256 = reinterpret_cast<const int4*>(meta_d + l.off_aw256);
     const int2* hw = reinterpret_cast<const int2*>(meta_d + l.off_hw);
-    auto gemm = [&](Epi epi, const CUtensorMap& ta, const CUtensorMap& tb, void* C, uint32_t N, uint32_t K) {
+    auto gemm = [&](Epi epi, const CUtensorMap& ta, const CUtensorMap& tb, void* C, uint32_t N, uint32_t K,
+                    const NormFuse* nf = nullptr) {
         prof_begin(PC_GEMM);
-        gemm_launch(stream, num_sms, opt.gemm_variant, epi, ta, tb, C, epi == Epi::GatedGeluF16 ? N / 2 : N, M, N, K);
+        gemm_launch(stream, num_sms, opt.gemm_variant, epi, ta, tb, C, epi == Epi::GatedGeluF16 ? N / 2 : N, M, N, K, nf);
         prof_end();
         stats.gemm_launches += 1;
         stats.gemm_flops += 2.0 * M * double(N) * K;
+    };
+    // h += acc, then xn = RMSNorm(h) * w: inside the GEMM's epilogue (the block's last N tile normalises it from L2) or as
+    // the stand-alone kernel - the same per-row code either way (norm.cuh), so the two are bit-identical
+    auto residual_gemm_then_norm = [&](const CUtensorMap& ta, const CUtensorMap& tb, uint32_t K, const float* w) {
+        if (opt.fuse_norm) {
+            const NormFuse nf{w, xn.as<__half>(), norm_cnt.as<uint32_t>(), hp.eps};
+            gemm(Epi::AddF32Norm, ta, tb, h.p, d, K, &nf);
+        } else {
+            gemm(Epi::AddF32, ta, tb, h.p, d, K);
+            prof_begin(PC_NORM);
+            launch_rmsnorm(stream, h.as<float>(), w, hp.eps, xn.as<__half>(), nullptr, M, d);
+            prof_end();
+        }
     };
     prof_begin(PC_NORM);
     launch_embed_rmsnorm(stream, ids, embd, layers[0].attn_norm, hp.eps, h.as<float>(), xn.as<__half>(), M, d, hp.n_vocab);
@@ -626,18 +642,17 @@ void DeviceCtx::forward(const MetaLayout& l, const int32_t* meta_d, uint8_t* let
                                 hp.max_distance);
         }
         prof_end();
-        gemm(Epi::AddF32, tm_ctx, L.tm_o, h.p, d, inner);
-        prof_begin(PC_NORM);
-        launch_rmsnorm(stream, h.as<float>(), L.ffn_norm, hp.eps, xn.as<__half>(), nullptr, M, d);
-        prof_end();
+        residual_gemm_then_norm(tm_ctx, L.tm_o, inner, L.ffn_norm);
         if (hp.gated) gemm(Epi::GatedGeluF16, tm_xn, L.tm_i, ffn.p, 2 * ff, d);
         else gemm(Epi::StoreF16Relu, tm_xn, L.tm_i, ffn.p, ff, d);
-        gemm(Epi::AddF32, tm_ffn, L.tm_down, h.p, d, ff);
-        const bool last = i + 1 == hp.n_layer;
-        prof_begin(PC_NORM);
-        launch_rmsnorm(stream, h.as<float>(), last ? out_norm : layers[i + 1].attn_norm, hp.eps, xn.as<__half>(),
-                       last ? hidden_f32 : nullptr, M, d);
-        prof_end();
+        if (i + 1 < hp.n_layer) {
+            residual_gemm_then_norm(tm_ffn, L.tm_down, ff, layers[i + 1].attn_norm);
+        } else {  // the final norm also leaves the fp32 hidden states for the debug entry: stand-alone kernel
+            gemm(Epi::AddF32, tm_ffn, L.tm_down, h.p, d, ff);
+            prof_begin(PC_NORM);
+            launch_rmsnorm(stream, h.as<float>(), out_norm, hp.eps, xn.as<__half>(), hidden_f32, M, d);
+            prof_end();
+        }
     }
     gemm(Epi::StoreF32, tm_xn, tm_c0, taps.p, hp.cnn_kernel * hp.cnn_hidden, d);
     prof_begin(PC_HEAD);

@@ -82,6 +82,8 @@ struct Options {
     int profile = 0;
     int attn_impl = 1;  // 1 = the product's tcgen05 kernel; 0, 2, 3 = A/B kernels of the debug library
     int map_rare_to_x = 1;  // U, Z, O, B tokenise as X (ProstT5's published preprocessing); 0 = their own tokens
+    int fuse_norm = 0;      // 1: the RMSNorm behind a residual add runs inside that GEMM's epilogue (bit-identical; measured
+                            // 4-5 % SLOWER than the separate kernel: profiles/r02/README.md)
 };
 
 class DeviceCtx;  // model.cu

@@ -76,5 +76,57 @@ __device__ __forceinline__ void rmsnorm_row(const float* __restrict__ h_row, con
     }
 }
 
+// kRows rows at once (rows row0 .. row0 + kRows - 1 of a matrix with leading dimension ld, those below n_valid only), for
+// d <= kMaxIter * 128: all the loads of all the rows are issued before the first reduction, so a warp working alone (the
+// GEMM epilogue that normalises a finished block) keeps kRows * 8 requests in flight instead of 8.  Per row the
+// arithmetic and its order are those of rmsnorm_row.
+template <bool kL2, int kRows>
+__device__ __forceinline__ void rmsnorm_rows(const float* __restrict__ h_row0, size_t ld, int n_valid, const float* __restrict__ w,
+                                             float eps, __half* __restrict__ xn_row0, uint32_t d, uint32_t lane) {
+    float4 v[kRows][kMaxIter];
+    const uint32_t n4 = d >> 2;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        const float4* hrow = reinterpret_cast<const float4*>(h_row0 + size_t(r) * ld);
+#pragma unroll
+        for (int it = 0; it < kMaxIter; ++it) {
+            const uint32_t c = it * 32 + lane;
+            if (r < n_valid && c < n4) v[r][it] = load4<kL2>(hrow + c);
+        }
+    }
+    float rs[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        float ss = 0.f;
+#pragma unroll
+        for (int it = 0; it < kMaxIter; ++it) {
+            const uint32_t c = it * 32 + lane;
+            if (r < n_valid && c < n4) {
+                const float4 x = v[r][it];
+                ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+            }
+        }
+        ss = warp_sum(ss);
+        rs[r] = rsqrtf(ss / float(d) + eps);
+    }
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+#pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+        const uint32_t c = it * 32 + lane;
+        if (c < n4) {
+            const float4 g = w4[c];
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                if (r < n_valid) {
+                    const float4 x = v[r][it];
+                    const float rr = rs[r];
+                    const float4 y = make_float4(x.x * rr * g.x, x.y * rr * g.y, x.z * rr * g.z, x.w * rr * g.w);
+                    store_half4(xn_row0 + size_t(r) * ld + c * 4, y.x, y.y, y.z, y.w);
+                }
+            }
+        }
+    }
+}
+
 }  // namespace norm
 }  // namespace p5
