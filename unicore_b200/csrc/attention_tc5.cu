@@ -246,24 +246,22 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, __half* __restric
                     // the tile, else the row's window of the table (offsets stay inside +-320)
                     const int dq_lo = j0 - (it.q0 + int(kBM) - 1), dq_hi = j0 + 31 - it.q0;  // chunk 0: min / max of j - i
                     const uint32_t er = es + uint32_t(int(kEHalf) - row_seq + j0) * 4;
-                    // one 32-column chunk: kind 0 = maximum pre-pass, 1 = the pass
-                    auto chunk = [&](const uint32_t (&v)[32], int c, int kind, float& acc, uint32_t* pkc, float2& s0, float2& s1) {
+                    // one 32-column chunk: kind 0 = maximum pre-pass, 1 = the pass.  A chunk cut by the end of the sequence
+                    // gets -inf scores beyond it (z = -inf, P = 0, sums and maxima unaffected): no masked code variants
+                    auto chunk = [&](uint32_t (&v)[32], int c, int kind, float& acc, uint32_t* pkc, float2& s0, float2& s1) {
                         const int lo = dq_lo + 32 * c, hi = dq_hi + 32 * c;
                         const bool bias_const = hi <= -128 || lo >= 128;
                         const float e_c = hi <= -128 ? e_lo : e_hi;
                         const uint32_t erc = er + uint32_t(c) * 128;
                         const int nvc = nv - 32 * c;
-                        if (nvc >= 32) {
-                            if (kind == 0) acc = bias_const ? softmax::chunk_row_max<false, false>(v, erc, e_c, nvc, acc)
-                                                            : softmax::chunk_row_max<true, false>(v, erc, e_c, nvc, acc);
-                            else if (bias_const) softmax::chunk_one_pass<false, false>(v, erc, e_c, m, nvc, pkc, s0, s1, acc);
-                            else softmax::chunk_one_pass<true, false>(v, erc, e_c, m, nvc, pkc, s0, s1, acc);
-                        } else {
-                            if (kind == 0) acc = bias_const ? softmax::chunk_row_max<false, true>(v, erc, e_c, nvc, acc)
-                                                            : softmax::chunk_row_max<true, true>(v, erc, e_c, nvc, acc);
-                            else if (bias_const) softmax::chunk_one_pass<false, true>(v, erc, e_c, m, nvc, pkc, s0, s1, acc);
-                            else softmax::chunk_one_pass<true, true>(v, erc, e_c, m, nvc, pkc, s0, s1, acc);
+                        if (nvc < 32) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = i < nvc ? v[i] : 0xff800000u;
                         }
+                        if (kind == 0) acc = bias_const ? softmax::chunk_row_max<false, false>(v, erc, e_c, 32, acc)
+                                                        : softmax::chunk_row_max<true, false>(v, erc, e_c, 32, acc);
+                        else if (bias_const) softmax::chunk_one_pass<false, false>(v, erc, e_c, m, 32, pkc, s0, s1, acc);
+                        else softmax::chunk_one_pass<true, false>(v, erc, e_c, m, 32, pkc, s0, s1, acc);
                     };
                     const int nc = (nv + 31) / 32;  // chunks that hold keys
                     float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
