@@ -16,10 +16,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--passes", type=int, default=1)
 ap.add_argument("--workload", default="config2")
 ap.add_argument("--n", type=int, default=None)
+ap.add_argument("--debug", action="store_true", help="load libprostt5_b200_debug.so (experiment knobs)")
 args = ap.parse_args()
 d = synth.model_dir(os.environ.get("P5_FULL_MODEL_DIR", "/tmp/p5_full_seed1"), spec.FULL, seed=1)
 aa, off = spec.synthetic_proteome(args.workload, n=args.n)
-with Predictor(d) as p:
+with Predictor(d, debug=args.debug) as p:
     p.stage(aa, off)
     for _ in range(args.passes):
         p.run_staged(None)

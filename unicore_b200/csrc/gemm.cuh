@@ -49,6 +49,7 @@ struct GemmShape {
     uint32_t idesc_extra;  // debug library only: OR-ed into the instruction descriptor (bf16 operand formats); bit 31 =
                            // skip the epilogue stores.  Always 0 in the product library.
     NormFuse norm;         // Epi::AddF32Norm
+    uint32_t multicast_a;  // CTA pairs that find themselves in an 8-CTA cluster share the A tile by TMA multicast (tma_aq)
 };
 
 // The "skip the epilogue stores" timing experiment exists in the debug library only: in the product build the test is
@@ -96,7 +97,8 @@ __device__ __forceinline__ void tile_coords(uint32_t t, uint32_t num_mt, uint32_
 template <int kCtaGroup, int kBlockN, int kStages, Epi kEpi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    const __grid_constant__ CUtensorMap tma_c, void* __restrict__ Cptr, GemmShape s) {
+                    const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_aq,
+                    void* __restrict__ Cptr, GemmShape s) {
     using L = GemmSmem<kCtaGroup, kBlockN, kStages>;
     constexpr uint32_t kUmmaM = kGemmBlockM * kCtaGroup;
     constexpr uint32_t kTmemCols = 2 * kBlockN;
@@ -123,17 +125,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const uint32_t cta_rank = cluster_rank & 1u;
     const uint32_t leader_rank = cluster_rank & ~1u;
     const bool is_leader = cta_rank == 0;
+    // A by multicast: in an 8-CTA cluster the four pairs work on the four N tiles of ONE row tile at the same time (host
+    // guarantees the geometry), so each CTA fetches a quarter (32 rows) of its 128 A rows per stage and multicasts it to
+    // the three CTAs of the same parity: a quarter of the L2 -> SM traffic for A.  A stage may then be overwritten only
+    // when ALL FOUR pairs have consumed it: every leader's commit arrives on the empty barriers of all eight CTAs.
+    const bool mc = kCtaGroup == 2 && s.multicast_a != 0u && ptx::cluster_nctarank() == 8u;
+    const uint32_t pair_in_cluster = cluster_rank >> 1;
 
     if (warp_idx == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tma_a);
         ptx::prefetch_tensormap(&tma_b);
         ptx::prefetch_tensormap(&tma_c);
+        ptx::prefetch_tensormap(&tma_aq);
     }
     if (warp_idx == 1 && lane == 0) {
 #pragma unroll
         for (int i = 0; i < kStages; ++i) {
             ptx::mbar_init(&full_bar[i], kCtaGroup);  // producer arrive of each CTA of the pair
-            ptx::mbar_init(&empty_bar[i], 1);         // one tcgen05.commit
+            ptx::mbar_init(&empty_bar[i], mc ? 4 : 1);  // one tcgen05.commit (per pair of the cluster when A is multicast)
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -176,7 +185,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         ptx::tma_load_2d(&tma_b, &full_bar[stage], sb, k_idx, n_idx, ptx::kEvictLast);
                     } else {
                         if (is_leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes * 2);
-                        ptx::tma_load_2d_pair(&tma_a, &full_bar[stage], sa, k_idx, m_idx, ptx::kEvictNormal);
+                        if (mc)
+                            ptx::tma_load_2d_pair_multicast(&tma_aq, &full_bar[stage], sa + pair_in_cluster * (L::kABytes / 4), k_idx,
+                                                            m_idx + int32_t(pair_in_cluster * (kGemmBlockM / 4)),
+                                                            uint16_t(0x55u << cta_rank), ptx::kEvictNormal);
+                        else
+                            ptx::tma_load_2d_pair(&tma_a, &full_bar[stage], sa, k_idx, m_idx, ptx::kEvictNormal);
                         ptx::tma_load_2d_pair(&tma_b, &full_bar[stage], sb, k_idx, n_idx, ptx::kEvictLast);
                         if (!is_leader) ptx::mbar_arrive_cluster(&full_bar[stage], leader_rank);
                     }
@@ -207,7 +221,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                             const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
                             ptx::umma_f16<kCtaGroup>(tmem_d, a_desc + koff, b_desc + koff, idesc, (kb | k) != 0u);
                         }
-                        ptx::umma_commit<kCtaGroup>(&empty_bar[stage], leader_rank);  // smem slot free when MMAs retire
+                        if (kCtaGroup == 2 && mc) ptx::umma_commit_mask(&empty_bar[stage], uint16_t(0xFFu));
+                        else ptx::umma_commit<kCtaGroup>(&empty_bar[stage], leader_rank);  // smem slot free when MMAs retire
                         if (kb == num_kb - 1) ptx::umma_commit<kCtaGroup>(&tmem_full_bar[as], leader_rank);
                     }
                     __syncwarp();

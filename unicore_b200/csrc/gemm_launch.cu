@@ -98,7 +98,8 @@ namespace {
 
 template <int kCtaGroup, int kBlockN, int kStages, Epi kEpi>
 void launch_one(cudaStream_t stream, int num_sms, const CUtensorMap& ta, const CUtensorMap& tb, void* C,
-                const GemmShape& s) {
+                const GemmShape& s_in, const CUtensorMap* taq) {
+    GemmShape s = s_in;
     const bool f16_out = (kEpi == Epi::StoreF16 || kEpi == Epi::StoreF16Relu || kEpi == Epi::GatedGeluF16);
     const CUtensorMap tc = make_c_tensor_map(C, f16_out, s.M, kEpi == Epi::GatedGeluF16 ? s.N / 2 : s.N, s.ldc);
     using L = GemmSmem<kCtaGroup, kBlockN, kStages>;
@@ -148,6 +149,12 @@ void launch_one(cudaStream_t stream, int num_sms, const CUtensorMap& ta, const C
             clusters = rounded;
             if (prefer) preferred_dim = cluster_ctas;
             else cluster_dim = cluster_ctas;
+            // The four pairs of a big cluster run the four N tiles of one row tile in the same round: A can be multicast
+            // (each CTA fetches a quarter of its A rows and sends it to the three CTAs of the same parity).  Measured
+            // (profiles/r02/README.md): correct, deterministic, -1 % on the two K-heavy projections alone, +0.2 % on the
+            // step = nothing; the L2 read sectors barely move.  Experiment knob of the debug library, off in the product.
+            static const bool mc_on = env_knob("P5_GEMM_MULTICAST", 0) != 0;
+            s.multicast_a = (mc_on && taq && cluster_ctas == 8 && num_nt % 4 == 0 && clusters % 4 == 0 && s.band_m == 1) ? 1u : 0u;
         }
     }
     cudaLaunchConfig_t cfg = {};
@@ -171,27 +178,28 @@ void launch_one(cudaStream_t stream, int num_sms, const CUtensorMap& ta, const C
         attr[1].val.preferredClusterDim.y = 1;
         attr[1].val.preferredClusterDim.z = 1;
         cfg.numAttrs = 2;
-        const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ta, tb, tc, C, s);
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ta, tb, tc, taq ? *taq : ta, C, s);
         if (e == cudaSuccess) return;
         if (e != cudaErrorInvalidValue && e != cudaErrorNotSupported) P5_CUDA(e);
         (void)cudaGetLastError();  // the plain pair launch below computes the same thing
         if (preferred_ok.exchange(false))
             fprintf(stderr, "prostt5_b200: preferred cluster dimension rejected (%s); using plain CTA pairs\n", cudaGetErrorString(e));
         cfg.numAttrs = 1;
+        s.multicast_a = 0;  // plain pairs: nothing to multicast to
     }
-    P5_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, tc, C, s));
+    P5_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, tc, taq ? *taq : ta, C, s));
 }
 
 template <int kCtaGroup, int kBlockN, int kStages>
 void launch_epi(cudaStream_t stream, int num_sms, Epi epi, const CUtensorMap& ta, const CUtensorMap& tb, void* C,
-                const GemmShape& s) {
+                const GemmShape& s, const CUtensorMap* taq) {
     switch (epi) {
-        case Epi::StoreF16: launch_one<kCtaGroup, kBlockN, kStages, Epi::StoreF16>(stream, num_sms, ta, tb, C, s); break;
-        case Epi::StoreF16Relu: launch_one<kCtaGroup, kBlockN, kStages, Epi::StoreF16Relu>(stream, num_sms, ta, tb, C, s); break;
-        case Epi::AddF32: launch_one<kCtaGroup, kBlockN, kStages, Epi::AddF32>(stream, num_sms, ta, tb, C, s); break;
-        case Epi::AddF32Norm: launch_one<kCtaGroup, kBlockN, kStages, Epi::AddF32Norm>(stream, num_sms, ta, tb, C, s); break;
-        case Epi::StoreF32: launch_one<kCtaGroup, kBlockN, kStages, Epi::StoreF32>(stream, num_sms, ta, tb, C, s); break;
-        case Epi::GatedGeluF16: launch_one<kCtaGroup, kBlockN, kStages, Epi::GatedGeluF16>(stream, num_sms, ta, tb, C, s); break;
+        case Epi::StoreF16: launch_one<kCtaGroup, kBlockN, kStages, Epi::StoreF16>(stream, num_sms, ta, tb, C, s, taq); break;
+        case Epi::StoreF16Relu: launch_one<kCtaGroup, kBlockN, kStages, Epi::StoreF16Relu>(stream, num_sms, ta, tb, C, s, taq); break;
+        case Epi::AddF32: launch_one<kCtaGroup, kBlockN, kStages, Epi::AddF32>(stream, num_sms, ta, tb, C, s, taq); break;
+        case Epi::AddF32Norm: launch_one<kCtaGroup, kBlockN, kStages, Epi::AddF32Norm>(stream, num_sms, ta, tb, C, s, taq); break;
+        case Epi::StoreF32: launch_one<kCtaGroup, kBlockN, kStages, Epi::StoreF32>(stream, num_sms, ta, tb, C, s, taq); break;
+        case Epi::GatedGeluF16: launch_one<kCtaGroup, kBlockN, kStages, Epi::GatedGeluF16>(stream, num_sms, ta, tb, C, s, taq); break;
     }
 }
 
@@ -233,7 +241,8 @@ uint32_t gemm_b_box_rows(int variant) {
 }
 
 void gemm_launch(cudaStream_t stream, int num_sms, int variant, Epi epi, const CUtensorMap& tma_a,
-                 const CUtensorMap& tma_b, void* C, uint32_t ldc, uint32_t M, uint32_t N, uint32_t K, const NormFuse* norm) {
+                 const CUtensorMap& tma_b, void* C, uint32_t ldc, uint32_t M, uint32_t N, uint32_t K, const NormFuse* norm,
+                 const CUtensorMap* tma_a_quarter) {
     P5_REQUIRE(epi != Epi::AddF32Norm || (norm && norm->w && norm->xn && norm->counters && N == ldc && N % 4 == 0), P5_ERR_ARG,
                "fused RMSNorm needs its weight, output and counters, and the whole row (N %u, ldc %u)", N, ldc);
     P5_REQUIRE(N % 8 == 0 && K % 8 == 0, P5_ERR_ARG, "GEMM N (%u) and K (%u) must be multiples of 8", N, K);
@@ -252,13 +261,13 @@ void gemm_launch(cudaStream_t stream, int num_sms, int variant, Epi epi, const C
     // skips the epilogue stores (timing experiments).  In the product library both are compiled out (common.h).
     static const uint32_t idesc_extra = (env_flag("P5_GEMM_BF16") ? ((1u << 7) | (1u << 10)) : 0u) |
                                         (env_flag("P5_GEMM_NOSTORE") ? (1u << 31) : 0u);
-    GemmShape s{M, N, K, ldc, band, idesc_extra, norm ? *norm : NormFuse{}};
+    GemmShape s{M, N, K, ldc, band, idesc_extra, norm ? *norm : NormFuse{}, 0u};
     if (M == 0 || N == 0) return;
     switch (variant) {
 #ifdef P5_DEBUG_BUILD
-        case 0: launch_epi<1, 256, 4>(stream, num_sms, epi, tma_a, tma_b, C, s); break;
+        case 0: launch_epi<1, 256, 4>(stream, num_sms, epi, tma_a, tma_b, C, s, nullptr); break;
 #endif
-        case 1: launch_epi<2, 256, 6>(stream, num_sms, epi, tma_a, tma_b, C, s); break;
+        case 1: launch_epi<2, 256, 6>(stream, num_sms, epi, tma_a, tma_b, C, s, tma_a_quarter); break;
         default: throw Error(P5_ERR_ARG, strf("GEMM variant %d is not built into this library", variant));
     }
 }

@@ -18,10 +18,11 @@ uint32_t gemm_b_box_rows(int variant);
 void gemm_init_device();  // once per device, with that device current
 
 // C[M,N] (op)= A[M,K] * B[N,K]^T with prebuilt tensor maps (weights keep theirs for the model lifetime)
+// tma_a_quarter: the A operand again with 32-row boxes; given, the pairs that land in 8-CTA clusters multicast A
 // norm: Epi::AddF32Norm only (the RMSNorm fused behind the residual add: needs N == ldc, the whole row)
 void gemm_launch(cudaStream_t stream, int num_sms, int variant, Epi epi, const CUtensorMap& tma_a,
                  const CUtensorMap& tma_b, void* C, uint32_t ldc, uint32_t M, uint32_t N, uint32_t K,
-                 const NormFuse* norm = nullptr);
+                 const NormFuse* norm = nullptr, const CUtensorMap* tma_a_quarter = nullptr);
 
 // convenience: builds both tensor maps
 void gemm_fp16(cudaStream_t stream, int num_sms, int variant, Epi epi, const void* A, uint32_t lda, const void* B,

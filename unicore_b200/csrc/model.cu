@@ -217,6 +217,7 @@ public:
     uint32_t cap = 0;
     DevBuf h, xn, qkv, ctx, ffn, taps, norm_cnt;
     CUtensorMap tm_xn, tm_ctx, tm_ffn, tm_q, tm_kv, tm_ctx_st;
+    CUtensorMap tm_ctx_q, tm_ffn_q;  // the A operands of the K-heavy projections again, 32-row boxes (A multicast in 8-CTA clusters)
 
     Slot slots[2];
     std::deque<DevBuf> staged_meta;   // one per staged batch on this device
@@ -548,6 +549,8 @@ void DeviceCtx::ensure_workspace(uint32_t tokens) {
     tm_xn = make_kmajor_tensor_map(xn.p, n, d, d, kGemmBlockM);
     tm_ctx = make_kmajor_tensor_map(ctx.p, n, inner, inner, kGemmBlockM);
     tm_ffn = make_kmajor_tensor_map(ffn.p, n, ff, ff, kGemmBlockM);
+    tm_ctx_q = make_kmajor_tensor_map(ctx.p, n, inner, inner, kGemmBlockM / 4);
+    tm_ffn_q = make_kmajor_tensor_map(ffn.p, n, ff, ff, kGemmBlockM / 4);
     tm_q = make_kmajor_tensor_map(qkv.p, n, 3 * inner, 3 * inner, kAttnTcBlockM);
     tm_kv = make_kmajor_tensor_map(qkv.p, n, 3 * inner, 3 * inner, 64);
     tm_ctx_st = make_attn_store_tensor_map(ctx.p, n, inner);
@@ -593,21 +596,21 @@ void DeviceCtx::forward(const MetaLayout& l, const int32_t* meta_d, uint8_t* let
     const int4* aw256 = reinterpret_cast<const int4*>(meta_d + l.off_aw256);
     const int2* hw = reinterpret_cast<const int2*>(meta_d + l.off_hw);
     auto gemm = [&](Epi epi, const CUtensorMap& ta, const CUtensorMap& tb, void* C, uint32_t N, uint32_t K,
-                    const NormFuse* nf = nullptr) {
+                    const NormFuse* nf = nullptr, const CUtensorMap* taq = nullptr) {
         prof_begin(PC_GEMM);
-        gemm_launch(stream, num_sms, opt.gemm_variant, epi, ta, tb, C, epi == Epi::GatedGeluF16 ? N / 2 : N, M, N, K, nf);
+        gemm_launch(stream, num_sms, opt.gemm_variant, epi, ta, tb, C, epi == Epi::GatedGeluF16 ? N / 2 : N, M, N, K, nf, taq);
         prof_end();
         stats.gemm_launches += 1;
         stats.gemm_flops += 2.0 * M * double(N) * K;
     };
     // h += acc, then xn = RMSNorm(h) * w: inside the GEMM's epilogue (the block's last N tile normalises it from L2) or as
     // the stand-alone kernel - the same per-row code either way (norm.cuh), so the two are bit-identical
-    auto residual_gemm_then_norm = [&](const CUtensorMap& ta, const CUtensorMap& tb, uint32_t K, const float* w) {
+    auto residual_gemm_then_norm = [&](const CUtensorMap& ta, const CUtensorMap& taq, const CUtensorMap& tb, uint32_t K, const float* w) {
         if (opt.fuse_norm) {
             const NormFuse nf{w, xn.as<__half>(), norm_cnt.as<uint32_t>(), hp.eps};
-            gemm(Epi::AddF32Norm, ta, tb, h.p, d, K, &nf);
+            gemm(Epi::AddF32Norm, ta, tb, h.p, d, K, &nf, &taq);
         } else {
-            gemm(Epi::AddF32, ta, tb, h.p, d, K);
+            gemm(Epi::AddF32, ta, tb, h.p, d, K, nullptr, &taq);
             prof_begin(PC_NORM);
             launch_rmsnorm(stream, h.as<float>(), w, hp.eps, xn.as<__half>(), nullptr, M, d);
             prof_end();
@@ -642,13 +645,13 @@ void DeviceCtx::forward(const MetaLayout& l, const int32_t* meta_d, uint8_t* let
                                 hp.max_distance);
         }
         prof_end();
-        residual_gemm_then_norm(tm_ctx, L.tm_o, inner, L.ffn_norm);
+        residual_gemm_then_norm(tm_ctx, tm_ctx_q, L.tm_o, inner, L.ffn_norm);
         if (hp.gated) gemm(Epi::GatedGeluF16, tm_xn, L.tm_i, ffn.p, 2 * ff, d);
         else gemm(Epi::StoreF16Relu, tm_xn, L.tm_i, ffn.p, ff, d);
         if (i + 1 < hp.n_layer) {
-            residual_gemm_then_norm(tm_ffn, L.tm_down, ff, layers[i + 1].attn_norm);
+            residual_gemm_then_norm(tm_ffn, tm_ffn_q, L.tm_down, ff, layers[i + 1].attn_norm);
         } else {  // the final norm also leaves the fp32 hidden states for the debug entry: stand-alone kernel
-            gemm(Epi::AddF32, tm_ffn, L.tm_down, h.p, d, ff);
+            gemm(Epi::AddF32, tm_ffn, L.tm_down, h.p, d, ff, nullptr, &tm_ffn_q);
             prof_begin(PC_NORM);
             launch_rmsnorm(stream, h.as<float>(), out_norm, hp.eps, xn.as<__half>(), hidden_f32, M, d);
             prof_end();

@@ -26,6 +26,11 @@ __device__ __forceinline__ uint32_t lane_id() {
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
     return l;
 }
+__device__ __forceinline__ uint32_t cluster_nctarank() {  // CTAs in this cluster
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -162,6 +167,19 @@ __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint64_t*
         : "memory");
 }
 
+// The same load MULTICAST to the CTAs of `mask` (bit i = CTA rank i of the cluster): the box lands at the same smem
+// offset in every destination CTA and each destination's transaction bytes are credited to the barrier at the same
+// offset in the even (leader) CTA of ITS pair.
+__device__ __forceinline__ void tma_load_2d_pair_multicast(const CUtensorMap* m, uint64_t* bar, void* smem, int32_t c0,
+                                                           int32_t c1, uint16_t mask, uint64_t hint) {
+    uint32_t bar_addr = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5, %6;" ::"r"(smem_u32(smem)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "h"(mask), "l"(hint)
+        : "memory");
+}
+
 // Plain (non-tensor) bulk copy global -> smem; `bytes` a multiple of 16, both addresses 16-byte aligned;
 // completion is credited to `bar` like a tensor load.
 __device__ __forceinline__ void bulk_load(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
@@ -270,6 +288,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar, uint32_t leader_rank 
             "h"(mask)
             : "memory");
     }
+}
+
+// cta_group::2 commit with an explicit CTA mask (the barrier at the same offset in every CTA of `mask`)
+__device__ __forceinline__ void umma_commit_mask(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
 }
 
 // TMEM -> registers: each lane of the warp reads its own TMEM lane (row), 32 consecutive columns.
