@@ -29,7 +29,7 @@ def summarize(lib):
             kernels[cur] = {op: 0 for op in OPS}
             kernels[cur]["instructions"] = 0
             continue
-        if cur and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+        if cur and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
             kernels[cur]["instructions"] += 1
             for op in OPS:
                 if re.search(r"\b" + re.escape(op), line):
