@@ -61,7 +61,7 @@ constexpr uint32_t kSmemStage = (kSmemE + 2 * kEPad * 4 + 511) / 512 * 512;  // 
 constexpr uint32_t kStageBytes = 32 * 64;                                     // 32 rows x 32 fp16 columns
 constexpr uint32_t kSmemBar = kSmemStage + 4 * kStageBytes;
 constexpr uint32_t kNumBars = 22;
-constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatBars = 8, kFeatOnePass = 16, kFeatPoly = 32;
+constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatBars = 8, kFeatOnePass = 16, kFeatPoly = 32, kFeatPrefetch = 1024;
 // timing-only ablations (debug library; WRONG results): 64 = every tile takes the constant-bias path (no LDS of the
 // table), 128 = the exponentials are replaced by one FMUL each (no MUFU)
 constexpr uint32_t kAblNoTable = 64, kAblNoEx2 = 128;
@@ -125,7 +125,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     const int4* __restrict__ work, uint32_t n_work, uint32_t n_items, uint32_t H,
                     const float* __restrict__ e_ext) {
     constexpr bool kTable = (kF & kFeatTable) != 0, kDefer = (kF & kFeatDefer) != 0, kStore = (kF & kFeatStore) != 0,
-                   kBars = (kF & kFeatBars) != 0, kOnePass = (kF & kFeatOnePass) != 0, kPoly = (kF & kFeatPoly) != 0;
+                   kBars = (kF & kFeatBars) != 0, kOnePass = (kF & kFeatOnePass) != 0, kPoly = (kF & kFeatPoly) != 0, kPrefetch = (kF & kFeatPrefetch) != 0;
     constexpr bool kNoTable = (kF & kAblNoTable) != 0, kNoEx2 = (kF & kAblNoEx2) != 0, kProf = (kF & kDbgProf) != 0, kNoMath = (kF & kAblNoMath) != 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -222,6 +222,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             uint32_t g = 0, n = 0;
             for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
                 const Item it = get_item(item, n_work, work);
+                if constexpr (kPrefetch) {
+                    // (debug library experiment) the NEXT item's Q and first K/V tile into L2 now: its loads, issued when
+                    // this item's last S has released the Q buffer, then pay an L2 hit instead of a DRAM miss
+                    if (item + gridDim.x < n_items) {
+                        const Item nx = get_item(item + gridDim.x, n_work, work);
+                        const int32_t qc = nx.h * int(kD);
+                        ptx::tma_prefetch_2d(&tm_q, qc, nx.tok0 + nx.q0);
+                        ptx::tma_prefetch_2d(&tm_q, qc + 64, nx.tok0 + nx.q0);
+                        for (uint32_t which = 1; which <= 2; ++which) {
+                            const int32_t col = int(which * H * kD) + nx.h * int(kD);
+                            ptx::tma_prefetch_2d(&tm_kv, col, nx.tok0);
+                            ptx::tma_prefetch_2d(&tm_kv, col + 64, nx.tok0);
+                        }
+                    }
+                }
                 load_q(it, n);
                 for (uint32_t j = 0; j < it.nt; ++j, ++g) {
                     load_kv(it, j, g, 0);
@@ -598,6 +613,7 @@ AttnKernel attn_kernel(uint32_t feat) {
         case 31 + 256: return attention_tc_kernel<31 + 256>;
         case 47 + 256: return attention_tc_kernel<47 + 256>;
         case 15 + 512: return attention_tc_kernel<15 + 512>;
+        case 15 + 1024: return attention_tc_kernel<15 + 1024>;
         case 15 + 768: return attention_tc_kernel<15 + 768>;
 #endif
         default: throw Error(P5_ERR_ARG, strf("attention feature mask %u is not built", feat));
@@ -607,7 +623,7 @@ AttnKernel attn_kernel(uint32_t feat) {
 
 void attention_tc_init_device() {
 #ifdef P5_DEBUG_BUILD
-    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u, 31u, 47u, 79u, 143u, 207u, 271u, 287u, 303u, 527u, 783u})
+    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u, 31u, 47u, 79u, 143u, 207u, 271u, 287u, 303u, 527u, 783u, 1039u})
 #else
     for (uint32_t f : {15u})
 #endif

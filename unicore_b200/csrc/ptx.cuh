@@ -145,6 +145,12 @@ constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+// L2 prefetch of a 2-D box (no smem destination, no completion signal)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
 // 2-D tiled load, completion signalled on `bar` of this CTA.
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* smem, int32_t c0, int32_t c1,
                                             uint64_t hint) {
