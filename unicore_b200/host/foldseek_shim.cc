@@ -63,6 +63,7 @@ int main(int argc, char** argv) {
         else if (a == "-v") g_verbosity = atoi(value().c_str());
         else if (a == "--prostt5-split-length") popt.split_len = uint32_t(atol(value().c_str()));  // default 1024 (host.h)
         else if (a == "--prostt5-rare-residues") popt.map_rare_to_x = value() == "own" ? 0 : 1;
+        else if (a == "--prostt5-head-eos") popt.head_include_eos = atoi(value().c_str()) != 0;
         else if (!a.empty() && a[0] == '-') { fprintf(stderr, "foldseek-b200: unknown option %s\n", a.c_str()); return 1; }
         else pos.push_back(a);
     }

@@ -637,6 +637,7 @@ static void apply_options(p5_model* m, const PredictOptions& opt, const std::vec
     if (opt.max_batch_tokens > 0 && p5_set_option(m, "max_batch_tokens", opt.max_batch_tokens) != 0)
         die(ERR_GENERAL, p5_last_error());
     if (opt.map_rare_to_x >= 0 && p5_set_option(m, "map_rare_to_x", opt.map_rare_to_x) != 0) die(ERR_GENERAL, p5_last_error());
+    if (opt.head_include_eos >= 0 && p5_set_option(m, "head_include_eos", opt.head_include_eos) != 0) die(ERR_GENERAL, p5_last_error());
     if (!talk) return;
     size_t n_long = 0;
     for (const Record& r : recs) n_long += opt.split_len > 0 && r.seq.size() > opt.split_len;

@@ -106,6 +106,7 @@ struct PredictOptions {
     // predicted in consecutive chunks.  0 = never split (full-length attention).
     uint32_t split_len = 1024;
     int map_rare_to_x = -1;  // -1 = library default (U, Z, O, B -> X)
+    int head_include_eos = -1;  // -1 = library default (the </s> row is part of the CNN head's input: SURVEY.md Q3)
     int64_t max_batch_tokens = 0;  // 0 = library default
     std::string stats_json;        // optional path
 };

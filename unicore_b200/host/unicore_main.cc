@@ -33,6 +33,7 @@ static const char* kUsage =
     "      --split-len <N>           Predict sequences longer than N residues in chunks of N [default: 1024, Foldseek's\n"
     "                                --prostt5-split-length default, which the reference relies on]; 0 = never split\n"
     "      --rare-residues <x|own>   U, Z, O, B tokenise as X (default, ProstT5's preprocessing) or as their own tokens\n"
+    "      --head-eos <0|1>          Whether the </s> row is part of the CNN head's input [default: 1]\n"
     "      --max-batch-tokens <N>    Tokens per forward pass\n"
     "      --stats-json <PATH>       Write throughput counters as JSON\n";
 
@@ -67,6 +68,7 @@ static int createdb(int argc, char** argv) {
             }
         } else if (a == "--procs") popt.procs = atoi(value("procs").c_str());
         else if (a == "--rare-residues") popt.map_rare_to_x = value("rare_residues") == "own" ? 0 : 1;
+        else if (a == "--head-eos") popt.head_include_eos = atoi(value("head_eos").c_str()) != 0;
         else if (a == "--split-len") popt.split_len = uint32_t(atol(value("split_len").c_str()));
         else if (a == "--max-batch-tokens") popt.max_batch_tokens = atol(value("max_batch_tokens").c_str());
         else if (a == "--stats-json") popt.stats_json = value("stats_json");
