@@ -197,6 +197,31 @@ def test_attention_table_ring_wraps_bit_identical():
     assert np.abs(outs[0].astype(np.float32) - _attention_ref(qkv, cu, H, bias, md)).max() < 6e-3
 
 
+def test_attention_table_slot_is_never_read_early():
+    """The race proof racecheck cannot give (it does not follow mbarrier complete_tx): with feature bit 2048 the TMA producer
+    fills a bias-table slot with NaN as soon as the four softmax warps have released it and only then issues the bulk load
+    of the next head's table.  A softmax warp that read the slot before its full-barrier phase would pull NaN into its
+    scores.  8 heads, fewer items per head than resident CTAs: every CTA changes head at every item (> 10^4 table loads
+    over the launch and its 5 repeats); ctx must be NaN-free and bit-identical to the unpoisoned kernel."""
+    lib = _lib.load_debug()
+    lens, H, md = _many_lens(9, 140, 20, 129), 8, 128
+    rng = np.random.default_rng(29)
+    cu = np.zeros(len(lens) + 1, np.int32)
+    cu[1:] = np.cumsum(lens)
+    M = int(cu[-1])
+    qkv = (rng.standard_normal((M, 3 * H * 128), dtype=np.float32) * 0.8).astype(np.float16)
+    bias = (rng.standard_normal((H, 2 * md + 1), dtype=np.float32) * 2.0).astype(np.float32)
+    outs = []
+    for impl in (16 + 15, 16 + 15 + 2048):
+        ctx = np.zeros((M, H * 128), np.float16)
+        ms = C.c_float(0)
+        _lib.check(lib.p5_dbg_attention(0, impl, qkv.ctypes.data, cu.ctypes.data, len(lens), H, md, bias.ctypes.data,
+                                        ctx.ctypes.data, 5, C.byref(ms)))
+        outs.append(ctx)
+    assert not np.isnan(outs[1].astype(np.float32)).any()
+    np.testing.assert_array_equal(outs[1].view(np.uint16), outs[0].view(np.uint16))
+
+
 @pytest.mark.parametrize("impl", _impls([6, 5, 4, 3, 2, 1, 0]))
 def test_attention_peaked_scores(impl):
     """Un-scaled T5 scores can be large: one dominant key per row must not overflow or lose the row."""

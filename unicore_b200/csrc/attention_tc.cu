@@ -61,7 +61,7 @@ constexpr uint32_t kSmemStage = (kSmemE + 2 * kEPad * 4 + 511) / 512 * 512;  // 
 constexpr uint32_t kStageBytes = 32 * 64;                                     // 32 rows x 32 fp16 columns
 constexpr uint32_t kSmemBar = kSmemStage + 4 * kStageBytes;
 constexpr uint32_t kNumBars = 22;
-constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatBars = 8, kFeatOnePass = 16, kFeatPoly = 32, kFeatPrefetch = 1024;
+constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatBars = 8, kFeatOnePass = 16, kFeatPoly = 32, kFeatPrefetch = 1024, kDbgPoison = 2048;
 // timing-only ablations (debug library; WRONG results): 64 = every tile takes the constant-bias path (no LDS of the
 // table), 128 = the exponentials are replaced by one FMUL each (no MUFU)
 constexpr uint32_t kAblNoTable = 64, kAblNoEx2 = 128;
@@ -125,7 +125,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     const int4* __restrict__ work, uint32_t n_work, uint32_t n_items, uint32_t H,
                     const float* __restrict__ e_ext) {
     constexpr bool kTable = (kF & kFeatTable) != 0, kDefer = (kF & kFeatDefer) != 0, kStore = (kF & kFeatStore) != 0,
-                   kBars = (kF & kFeatBars) != 0, kOnePass = (kF & kFeatOnePass) != 0, kPoly = (kF & kFeatPoly) != 0, kPrefetch = (kF & kFeatPrefetch) != 0;
+                   kBars = (kF & kFeatBars) != 0, kOnePass = (kF & kFeatOnePass) != 0, kPoly = (kF & kFeatPoly) != 0, kPrefetch = (kF & kFeatPrefetch) != 0, kPoison = (kF & kDbgPoison) != 0;
     constexpr bool kNoTable = (kF & kAblNoTable) != 0, kNoEx2 = (kF & kAblNoEx2) != 0, kProf = (kF & kDbgProf) != 0, kNoMath = (kF & kAblNoMath) != 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -196,6 +196,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                         cur_h = it.h;
                         const uint32_t sl = ek & 1;
                         if (ek >= 2) ptx::mbar_wait(&e_empty[sl], ((ek >> 1) & 1) ^ 1);
+                        if constexpr (kPoison) {
+                            // (debug library, test_attention_table_slot_is_never_read_early) the slot is free: fill it with
+                            // NaN before the bulk load lands.  A softmax warp that read the slot before its e_full phase -
+                            // the hazard compute-sanitizer's racecheck reports because it does not model complete_tx -
+                            // would carry the NaN into its scores and so into ctx.
+                            for (uint32_t i = 0; i < kEPad; ++i) sts_f32(e_smem + (sl * kEPad + i) * 4, __int_as_float(0x7fc00000));
+                            ptx::fence_proxy_async_smem();
+                        }
                         ptx::mbar_arrive_expect_tx(&e_full[sl], kEPad * 4);
                         ptx::bulk_load(smem + kSmemE + sl * kEPad * 4, e_ext + size_t(it.h) * kEPad, kEPad * 4, &e_full[sl]);
                         ++ek;
@@ -614,6 +622,7 @@ AttnKernel attn_kernel(uint32_t feat) {
         case 47 + 256: return attention_tc_kernel<47 + 256>;
         case 15 + 512: return attention_tc_kernel<15 + 512>;
         case 15 + 1024: return attention_tc_kernel<15 + 1024>;
+        case 15 + 2048: return attention_tc_kernel<15 + 2048>;
         case 15 + 768: return attention_tc_kernel<15 + 768>;
 #endif
         default: throw Error(P5_ERR_ARG, strf("attention feature mask %u is not built", feat));
@@ -623,7 +632,7 @@ AttnKernel attn_kernel(uint32_t feat) {
 
 void attention_tc_init_device() {
 #ifdef P5_DEBUG_BUILD
-    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u, 31u, 47u, 79u, 143u, 207u, 271u, 287u, 303u, 527u, 783u, 1039u})
+    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u, 31u, 47u, 79u, 143u, 207u, 271u, 287u, 303u, 527u, 783u, 1039u, 2063u})
 #else
     for (uint32_t f : {15u})
 #endif
