@@ -61,7 +61,7 @@ constexpr uint32_t kSmemStage = (kSmemE + 2 * kEPad * 4 + 511) / 512 * 512;  // 
 constexpr uint32_t kStageBytes = 32 * 64;                                     // 32 rows x 32 fp16 columns
 constexpr uint32_t kSmemBar = kSmemStage + 4 * kStageBytes;
 constexpr uint32_t kNumBars = 22;
-constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatBars = 8, kFeatOnePass = 16, kFeatPoly = 32, kFeatPrefetch = 1024, kDbgPoison = 2048;
+constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatBars = 8, kFeatOnePass = 16, kFeatPoly = 32, kFeatPrefetch = 1024, kDbgPoison = 2048, kFeatLate = 4096;
 // timing-only ablations (debug library; WRONG results): 64 = every tile takes the constant-bias path (no LDS of the
 // table), 128 = the exponentials are replaced by one FMUL each (no MUFU)
 constexpr uint32_t kAblNoTable = 64, kAblNoEx2 = 128;
@@ -125,7 +125,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     const int4* __restrict__ work, uint32_t n_work, uint32_t n_items, uint32_t H,
                     const float* __restrict__ e_ext) {
     constexpr bool kTable = (kF & kFeatTable) != 0, kDefer = (kF & kFeatDefer) != 0, kStore = (kF & kFeatStore) != 0,
-                   kBars = (kF & kFeatBars) != 0, kOnePass = (kF & kFeatOnePass) != 0, kPoly = (kF & kFeatPoly) != 0, kPrefetch = (kF & kFeatPrefetch) != 0, kPoison = (kF & kDbgPoison) != 0;
+                   kBars = (kF & kFeatBars) != 0, kOnePass = (kF & kFeatOnePass) != 0, kPoly = (kF & kFeatPoly) != 0, kPrefetch = (kF & kFeatPrefetch) != 0, kPoison = (kF & kDbgPoison) != 0, kLate = (kF & kFeatLate) != 0;
     constexpr bool kNoTable = (kF & kAblNoTable) != 0, kNoEx2 = (kF & kAblNoEx2) != 0, kProf = (kF & kDbgProf) != 0, kNoMath = (kF & kAblNoMath) != 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -334,6 +334,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if constexpr (kProf) tp = uint32_t(clock());
         [[maybe_unused]] const uint32_t t_begin = tp;
 
+        // kFeatLate: the P store of a tile is only WAITED for (tcgen05.wait::st) and announced (p_full) after the next
+        // tile's tcgen05.ld has been issued, so the store's latency and the load's overlap; same instructions, same bits.
+        bool owe = false;
+        uint32_t owe_b = 0;
+        auto flush_p = [&]() {
+            if (owe) {
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&p_full[owe_b]);
+                owe = false;
+            }
+        };
         // O / l -> ctx for the item whose tiles ended at global tile index g_end (exclusive).
         //   row0 = first token row of this warp's 32 rows, valid = how many of them belong to the sequence
         auto epilogue = [&](float inv, int row0, int valid, int h, uint32_t g_end, uint32_t nt) {
@@ -424,6 +437,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 if constexpr (kProf) pc[10] += warp_valid ? 1u : 0u;
                 uint32_t pk[32];
                 if (kNoMath || !warp_valid) {  // all 32 query rows lie past the end of the sequence: keep the protocol going only
+                    if constexpr (kLate) flush_p();
 #pragma unroll
                     for (int c = 0; c < 32; ++c) pk[c] = 0u;
                 } else {
@@ -435,6 +449,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 uint32_t v0[32], v1[32];
                 ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN, v0);
                 ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN + 32, v1);
+                if constexpr (kLate) flush_p();  // the previous tile's P: its store has had the loads' issue time to land
                 ptx::tmem_ld_wait();
                 tick(1);
                 bool two_pass = true;
@@ -551,10 +566,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 }
                 }
                 ptx::tmem_st_32x32b_x32(t_lane + 128 + b * kBN, pk);  // P over the first 32 columns of S
-                ptx::tmem_st_wait();
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&p_full[b]);
+                if constexpr (kLate) {
+                    owe = true;
+                    owe_b = b;
+                    if (j + 1 == it.nt || (kDefer && j == 0 && pend)) flush_p();  // nothing follows at once: announce it now
+                } else {
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&p_full[b]);
+                }
                 if constexpr (kDefer) {
                     // the previous item's epilogue runs here, behind this item's first tile: its last P.V has had a
                     // whole softmax tile of time to drain, and the tensor pipe already holds this item's next S
@@ -623,6 +644,7 @@ AttnKernel attn_kernel(uint32_t feat) {
         case 15 + 512: return attention_tc_kernel<15 + 512>;
         case 15 + 1024: return attention_tc_kernel<15 + 1024>;
         case 15 + 2048: return attention_tc_kernel<15 + 2048>;
+        case 15 + 4096: return attention_tc_kernel<15 + 4096>;
         case 15 + 768: return attention_tc_kernel<15 + 768>;
 #endif
         default: throw Error(P5_ERR_ARG, strf("attention feature mask %u is not built", feat));
@@ -632,7 +654,7 @@ AttnKernel attn_kernel(uint32_t feat) {
 
 void attention_tc_init_device() {
 #ifdef P5_DEBUG_BUILD
-    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u, 31u, 47u, 79u, 143u, 207u, 271u, 287u, 303u, 527u, 783u, 1039u, 2063u})
+    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u, 31u, 47u, 79u, 143u, 207u, 271u, 287u, 303u, 527u, 783u, 1039u, 2063u, 4111u})
 #else
     for (uint32_t f : {15u})
 #endif
