@@ -61,7 +61,7 @@ constexpr uint32_t kSmemStage = (kSmemE + 2 * kEPad * 4 + 511) / 512 * 512;  // 
 constexpr uint32_t kStageBytes = 32 * 64;                                     // 32 rows x 32 fp16 columns
 constexpr uint32_t kSmemBar = kSmemStage + 4 * kStageBytes;
 constexpr uint32_t kNumBars = 22;
-constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatBars = 8, kFeatOnePass = 16, kFeatPoly = 32, kFeatPrefetch = 1024, kDbgPoison = 2048, kFeatLate = 4096;
+constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatBars = 8, kFeatOnePass = 16, kFeatPoly = 32, kFeatPrefetch = 1024, kDbgPoison = 2048, kFeatLate = 4096, kFeatNarrow = 8192;
 // timing-only ablations (debug library; WRONG results): 64 = every tile takes the constant-bias path (no LDS of the
 // table), 128 = the exponentials are replaced by one FMUL each (no MUFU)
 constexpr uint32_t kAblNoTable = 64, kAblNoEx2 = 128;
@@ -125,7 +125,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     const int4* __restrict__ work, uint32_t n_work, uint32_t n_items, uint32_t H,
                     const float* __restrict__ e_ext) {
     constexpr bool kTable = (kF & kFeatTable) != 0, kDefer = (kF & kFeatDefer) != 0, kStore = (kF & kFeatStore) != 0,
-                   kBars = (kF & kFeatBars) != 0, kOnePass = (kF & kFeatOnePass) != 0, kPoly = (kF & kFeatPoly) != 0, kPrefetch = (kF & kFeatPrefetch) != 0, kPoison = (kF & kDbgPoison) != 0, kLate = (kF & kFeatLate) != 0;
+                   kBars = (kF & kFeatBars) != 0, kOnePass = (kF & kFeatOnePass) != 0, kPoly = (kF & kFeatPoly) != 0, kPrefetch = (kF & kFeatPrefetch) != 0, kPoison = (kF & kDbgPoison) != 0, kLate = (kF & kFeatLate) != 0, kNarrow = (kF & kFeatNarrow) != 0;
     constexpr bool kNoTable = (kF & kAblNoTable) != 0, kNoEx2 = (kF & kAblNoEx2) != 0, kProf = (kF & kDbgProf) != 0, kNoMath = (kF & kAblNoMath) != 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -259,7 +259,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             constexpr uint32_t idesc_pv = ptx::make_idesc_f16_f32(kBM, kD) | ptx::kIdescBMnMajor;
             uint32_t g = 0, n = 0;
             // O += P_gg . V_gg   (gg = global tile index, jj = its index inside item number nn of this CTA)
-            auto issue_pv = [&](uint32_t gg, uint32_t jj, uint32_t nn) {
+            auto issue_pv = [&](uint32_t gg, uint32_t jj, uint32_t nn, uint32_t n_ks) {
                 const uint32_t st = gg & 1, ph = (gg >> 1) & 1;
                 ptx::mbar_wait(&v_full[st], ph);
                 ptx::mbar_wait(&p_full[st], ph);
@@ -269,6 +269,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
                 for (uint32_t ks = 0; ks < kBN / 16; ++ks) {
                     // 16 keys per step = two 8-row groups of the MN-major V tile (2 x 1024 B)
+                    if (kNarrow && ks >= n_ks) break;  // (kFeatNarrow) keys past the end of the sequence have P = 0 exactly
                     const uint64_t b = ptx::make_mnmajor_sw128_desc(sV + st * kKVBytes + ks * 2048, kKVBytes / 2, 1024);
                     ptx::umma_f16_ts(tmem_base, a_tmem + ks * 8, b, idesc_pv, (jj | ks) != 0u);
                 }
@@ -276,7 +277,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 ptx::umma_commit<1>(&pv_done[st]);
             };
             bool have_prev = false;  // kDefer: tile g-1 (possibly of the previous item) still owes its P.V
-            uint32_t prev_jj = 0, prev_n = 0;
+            uint32_t prev_jj = 0, prev_n = 0, prev_ks = kBN / 16;
             for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
                 const Item it = get_item(item, n_work, work);
                 ptx::mbar_wait(q_full, n & 1);
@@ -296,19 +297,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     if constexpr (!kBars) ptx::umma_commit<1>(&k_empty[st]);
                     ptx::umma_commit<1>(&s_full[st]);
                     if (j + 1 == it.nt) ptx::umma_commit<1>(q_empty);
+                    // 16-key steps of this tile that hold keys (all four except in an item's last tile)
+                    const uint32_t ks_here = min(kBN / 16, (uint32_t(it.T) - j * kBN + 15u) / 16u);
                     if constexpr (kDefer) {
-                        if (have_prev) issue_pv(g - 1, prev_jj, prev_n);
+                        if (have_prev) issue_pv(g - 1, prev_jj, prev_n, prev_ks);
                         have_prev = true;
                         prev_jj = j;
                         prev_n = n;
+                        prev_ks = ks_here;
                     } else {
-                        if (j >= 1) issue_pv(g - 1, j - 1, n);
+                        if (j >= 1) issue_pv(g - 1, j - 1, n, kBN / 16);
+                        prev_ks = ks_here;
                     }
                 }
-                if constexpr (!kDefer) issue_pv(g - 1, it.nt - 1, n);
+                if constexpr (!kDefer) issue_pv(g - 1, it.nt - 1, n, prev_ks);
             }
             if constexpr (kDefer) {
-                if (have_prev) issue_pv(g - 1, prev_jj, prev_n);
+                if (have_prev) issue_pv(g - 1, prev_jj, prev_n, prev_ks);
             }
         }
     } else {
@@ -447,8 +452,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 const float e_c = dmax <= -128 ? e_lo : e_hi;
                 const uint32_t er = es + uint32_t(int(kEHalf) - row_seq + j0) * 4;
                 uint32_t v0[32], v1[32];
+                // (kFeatNarrow) an item's last tile with at most 32 keys: the second 32 columns are never read or computed
+                const bool half_only = kNarrow && it.T - j0 <= 32;
                 ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN, v0);
-                ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN + 32, v1);
+                if (!half_only) ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN + 32, v1);
                 if constexpr (kLate) flush_p();  // the previous tile's P: its store has had the loads' issue time to land
                 ptx::tmem_ld_wait();
                 tick(1);
@@ -473,7 +480,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 }
                 if (two_pass) {
                 float z[64];
-                if (bias_const) {
+                if (half_only) {
+                    if (bias_const) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) z[c] = fmaf(__uint_as_float(v0[c]), kLog2e, e_c);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) z[c] = fmaf(__uint_as_float(v0[c]), kLog2e, lds_f32(er + c * 4));
+                    }
+#pragma unroll
+                    for (int c = 32; c < 64; ++c) z[c] = -INFINITY;
+                } else if (bias_const) {
                     const float e = e_c;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
@@ -545,6 +562,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                         pk[q + 1] = pack_h2(c2.x, c2.y);
                     }
                     sa = s0.x; sb = s0.y; sc = s1.x; sd = s1.y;
+                } else if (half_only) {  // columns 32..63 hold no keys: P = 0 there, exactly what 2^(-inf - m) gives
+#pragma unroll
+                    for (int c = 0; c < 16; c += 2) {
+                        const float p0 = ex2(z[2 * c] - m), p1 = ex2(z[2 * c + 1] - m);
+                        const float p2 = ex2(z[2 * c + 2] - m), p3 = ex2(z[2 * c + 3] - m);
+                        sa += p0; sb += p1; sc += p2; sd += p3;
+                        pk[c] = pack_h2(p0, p1);
+                        pk[c + 1] = pack_h2(p2, p3);
+                    }
+#pragma unroll
+                    for (int c = 16; c < 32; ++c) pk[c] = 0u;
                 } else {
 #pragma unroll
                 for (int c = 0; c < 32; c += 2) {
@@ -645,6 +673,7 @@ AttnKernel attn_kernel(uint32_t feat) {
         case 15 + 1024: return attention_tc_kernel<15 + 1024>;
         case 15 + 2048: return attention_tc_kernel<15 + 2048>;
         case 15 + 4096: return attention_tc_kernel<15 + 4096>;
+        case 15 + 8192: return attention_tc_kernel<15 + 8192>;
         case 15 + 768: return attention_tc_kernel<15 + 768>;
 #endif
         default: throw Error(P5_ERR_ARG, strf("attention feature mask %u is not built", feat));
@@ -654,7 +683,7 @@ AttnKernel attn_kernel(uint32_t feat) {
 
 void attention_tc_init_device() {
 #ifdef P5_DEBUG_BUILD
-    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u, 31u, 47u, 79u, 143u, 207u, 271u, 287u, 303u, 527u, 783u, 1039u, 2063u, 4111u})
+    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u, 31u, 47u, 79u, 143u, 207u, 271u, 287u, 303u, 527u, 783u, 1039u, 2063u, 4111u, 8207u})
 #else
     for (uint32_t f : {15u})
 #endif
