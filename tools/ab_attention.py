@@ -56,15 +56,15 @@ def main():
         flops = 4.0 * 128 * H * float(sum(t * t for t in lens))
         base = None
         row = {}
-        for impl in (16, 31, 47, 63, 16 + 15 + 1024, 16 + 15 + 4096, 16 + 15 + 8192, 6, 5, 4, 2, 3, 0):
+        for impl in (16, 31, 47, 63, 16 + 15 + 1024, 16 + 15 + 4096, 16 + 15 + 8192, 16 + 15 + 16384, 6, 5, 4, 2, 3, 0):
             ctx, ms = run(lib, impl, qkv, cu, H, bias, a.iters)
             if base is None:
                 base = ctx
-            same = bool(np.array_equal(ctx.view(np.uint16), base.view(np.uint16))) if impl in (16, 31, 16 + 15 + 1024, 16 + 15 + 4096, 16 + 15 + 8192) else None
+            same = bool(np.array_equal(ctx.view(np.uint16), base.view(np.uint16))) if impl in (16, 31, 16 + 15 + 1024, 16 + 15 + 4096, 16 + 15 + 8192, 16 + 15 + 16384) else None
             if impl in (2, 3, 4, 5, 6, 47, 63):  # different summation order of the row sums: compare within fp16 noise
                 row["impl%d_maxdiff_vs_mask0" % impl] = float(np.abs(ctx.astype(np.float32) - base.astype(np.float32)).max())
             row["impl%d" % impl] = {"ms": ms, "tflops": flops / ms * 1e-9, "bit_identical_to_mask0": same}
-            print("%-34s impl %4d  %.3f ms  %6.1f TFLOP/s  same=%s" % (name, impl, ms, flops / ms * 1e-9, same), flush=True)
+            print("%-34s impl %5d  %.3f ms  %6.1f TFLOP/s  same=%s" % (name, impl, ms, flops / ms * 1e-9, same), flush=True)
         res[name] = {"tokens": M, "flops": flops, "variants": row}
     if a.out:
         with open(a.out, "w") as f:

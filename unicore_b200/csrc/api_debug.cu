@@ -140,7 +140,7 @@ extern "C" int p5_dbg_attention(int device, int impl, const uint16_t* qkv_host, 
         attention_tc5_init_device();
         attention_tc6_init_device();
         // impl 2 = second-generation tcgen05 kernel (two softmax warpgroups per item); impl 16 + f = tcgen05 kernel with feature mask f (attention_tc.cu), for A/B tests of the pipelining features
-        P5_REQUIRE((impl >= 0 && impl <= 6) || impl == 8 || (impl >= 16 && impl < 16 + 16384), P5_ERR_ARG,
+        P5_REQUIRE((impl >= 0 && impl <= 6) || impl == 8 || (impl >= 16 && impl < 16 + 32768), P5_ERR_ARG,
                    "impl must be 0 (mma.sync), 1 (tcgen05), 2 (two softmax warpgroups), 3 (packed-pair math), 4 (query-tile pairs; 8 = with phase counters), 5 (128-key tiles), 6 (eight softmax warps) "
                    "or 16..31 (first tcgen05 kernel with an explicit feature mask)");
         const int features = impl >= 16 ? impl - 16 : -1;

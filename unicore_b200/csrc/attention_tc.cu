@@ -61,7 +61,7 @@ constexpr uint32_t kSmemStage = (kSmemE + 2 * kEPad * 4 + 511) / 512 * 512;  // 
 constexpr uint32_t kStageBytes = 32 * 64;                                     // 32 rows x 32 fp16 columns
 constexpr uint32_t kSmemBar = kSmemStage + 4 * kStageBytes;
 constexpr uint32_t kNumBars = 22;
-constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatBars = 8, kFeatOnePass = 16, kFeatPoly = 32, kFeatPrefetch = 1024, kDbgPoison = 2048, kFeatLate = 4096, kFeatNarrow = 8192;
+constexpr uint32_t kFeatTable = 1, kFeatDefer = 2, kFeatStore = 4, kFeatBars = 8, kFeatOnePass = 16, kFeatPoly = 32, kFeatPrefetch = 1024, kDbgPoison = 2048, kFeatLate = 4096, kFeatNarrow = 8192, kFeatRegs = 16384;
 // timing-only ablations (debug library; WRONG results): 64 = every tile takes the constant-bias path (no LDS of the
 // table), 128 = the exponentials are replaced by one FMUL each (no MUFU)
 constexpr uint32_t kAblNoTable = 64, kAblNoEx2 = 128;
@@ -119,13 +119,13 @@ __device__ __forceinline__ Item get_item(uint32_t item, uint32_t n_work, const i
 }
 
 template <uint32_t kF>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__((kF & kFeatRegs) ? 256u : kThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                     const __grid_constant__ CUtensorMap tm_ctx, __half* __restrict__ ctx,
                     const int4* __restrict__ work, uint32_t n_work, uint32_t n_items, uint32_t H,
                     const float* __restrict__ e_ext) {
     constexpr bool kTable = (kF & kFeatTable) != 0, kDefer = (kF & kFeatDefer) != 0, kStore = (kF & kFeatStore) != 0,
-                   kBars = (kF & kFeatBars) != 0, kOnePass = (kF & kFeatOnePass) != 0, kPoly = (kF & kFeatPoly) != 0, kPrefetch = (kF & kFeatPrefetch) != 0, kPoison = (kF & kDbgPoison) != 0, kLate = (kF & kFeatLate) != 0, kNarrow = (kF & kFeatNarrow) != 0;
+                   kBars = (kF & kFeatBars) != 0, kOnePass = (kF & kFeatOnePass) != 0, kPoly = (kF & kFeatPoly) != 0, kPrefetch = (kF & kFeatPrefetch) != 0, kPoison = (kF & kDbgPoison) != 0, kLate = (kF & kFeatLate) != 0, kNarrow = (kF & kFeatNarrow) != 0, kRegs = (kF & kFeatRegs) != 0;
     constexpr bool kNoTable = (kF & kAblNoTable) != 0, kNoEx2 = (kF & kAblNoEx2) != 0, kProf = (kF & kDbgProf) != 0, kNoMath = (kF & kAblNoMath) != 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -180,6 +180,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
+    // kFeatRegs (debug library experiment): 256 threads, the softmax warpgroup takes the registers the producer / MMA
+    // warpgroup (two working threads, two idle warps) does not need: 216 instead of 168 per softmax thread, enough to
+    // hold the NEXT key tile's scores while this one is in the exp loop
+    if constexpr (kRegs) {
+        if (warp >= 4) ptx::setmaxnreg_dec<40>();
+    }
     const uint32_t sQ = ptx::smem_u32(smem + kSmemQ);
     const uint32_t sK = ptx::smem_u32(smem + kSmemK);
     const uint32_t sV = ptx::smem_u32(smem + kSmemV);
@@ -316,8 +322,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 if (have_prev) issue_pv(g - 1, prev_jj, prev_n, prev_ks);
             }
         }
-    } else {
+    } else if (warp < 4) {
         // =============================== softmax warps ===============================
+        if constexpr (kRegs) ptx::setmaxnreg_inc<216>();
         const uint32_t r = warp * 32 + lane;  // row of the tile == TMEM lane
         const uint32_t t_lane = tmem_base + ((warp * 32u) << 16);
         uint8_t* stage = smem + kSmemStage + warp * kStageBytes;
@@ -341,6 +348,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
         // kFeatLate: the P store of a tile is only WAITED for (tcgen05.wait::st) and announced (p_full) after the next
         // tile's tcgen05.ld has been issued, so the store's latency and the load's overlap; same instructions, same bits.
+        // kFeatRegs: S of the NEXT tile of the item, loaded into registers as soon as it exists (probed without blocking)
+        [[maybe_unused]] uint32_t vn0[32], vn1[32];
+        [[maybe_unused]] bool have_next = false;
         bool owe = false;
         uint32_t owe_b = 0;
         auto flush_p = [&]() {
@@ -436,8 +446,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 const uint32_t b = g & 1, ph = (g >> 1) & 1;
                 const int j0 = int(j * kBN);
                 tick(j == 0 ? 8 : 5);
-                ptx::mbar_wait(&s_full[b], ph);
-                ptx::tc_fence_after();
+                if (!(kRegs && have_next)) {  // (else: already observed when its scores were prefetched)
+                    ptx::mbar_wait(&s_full[b], ph);
+                    ptx::tc_fence_after();
+                }
                 tick(0);
                 if constexpr (kProf) pc[10] += warp_valid ? 1u : 0u;
                 uint32_t pk[32];
@@ -454,10 +466,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 uint32_t v0[32], v1[32];
                 // (kFeatNarrow) an item's last tile with at most 32 keys: the second 32 columns are never read or computed
                 const bool half_only = kNarrow && it.T - j0 <= 32;
-                ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN, v0);
-                if (!half_only) ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN + 32, v1);
-                if constexpr (kLate) flush_p();  // the previous tile's P: its store has had the loads' issue time to land
-                ptx::tmem_ld_wait();
+                if (kRegs && have_next) {
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        v0[c] = vn0[c];
+                        v1[c] = vn1[c];
+                    }
+                    have_next = false;
+                } else {
+                    ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN, v0);
+                    if (!half_only) ptx::tmem_ld_32x32b_x32(t_lane + 128 + b * kBN + 32, v1);
+                    if constexpr (kLate) flush_p();  // the previous tile's P: its store has had the loads' issue time to land
+                    ptx::tmem_ld_wait();
+                }
+                if constexpr (kRegs) {
+                    // the next tile's scores, if the tensor pipe has already delivered them (it runs one tile ahead)
+                    if (j + 1 < it.nt && ptx::mbar_test_wait(&s_full[(g + 1) & 1], ((g + 1) >> 1) & 1)) {
+                        ptx::tc_fence_after();
+                        ptx::tmem_ld_32x32b_x32(t_lane + 128 + ((g + 1) & 1) * kBN, vn0);
+                        ptx::tmem_ld_32x32b_x32(t_lane + 128 + ((g + 1) & 1) * kBN + 32, vn1);
+                        have_next = true;
+                    }
+                }
                 tick(1);
                 bool two_pass = true;
                 if constexpr (kOnePass) {
@@ -674,6 +705,7 @@ AttnKernel attn_kernel(uint32_t feat) {
         case 15 + 2048: return attention_tc_kernel<15 + 2048>;
         case 15 + 4096: return attention_tc_kernel<15 + 4096>;
         case 15 + 8192: return attention_tc_kernel<15 + 8192>;
+        case 15 + 16384: return attention_tc_kernel<15 + 16384>;
         case 15 + 768: return attention_tc_kernel<15 + 768>;
 #endif
         default: throw Error(P5_ERR_ARG, strf("attention feature mask %u is not built", feat));
@@ -683,7 +715,7 @@ AttnKernel attn_kernel(uint32_t feat) {
 
 void attention_tc_init_device() {
 #ifdef P5_DEBUG_BUILD
-    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u, 31u, 47u, 79u, 143u, 207u, 271u, 287u, 303u, 527u, 783u, 1039u, 2063u, 4111u, 8207u})
+    for (uint32_t f : {0u, 1u, 2u, 4u, 7u, 8u, 14u, 15u, 31u, 47u, 79u, 143u, 207u, 271u, 287u, 303u, 527u, 783u, 1039u, 2063u, 4111u, 8207u, 16399u})
 #else
     for (uint32_t f : {15u})
 #endif
@@ -728,7 +760,7 @@ void launch_attention_tc(cudaStream_t st, int num_sms, const CUtensorMap& tm_q, 
     static const int ctas_per_sm = env_knob("P5_ATTN_CTAS", 2);  // experiment knob (debug library only)
     const uint32_t grid = uint32_t(std::min<uint64_t>(n_items, uint64_t(ctas_per_sm * num_sms)));
     const uint32_t feat = uint32_t(features < 0 ? attention_tc_default_features() : features);
-    attn_kernel(feat)<<<grid, kThreads, kSmemDynamic, st>>>(tm_q, tm_kv, tm_ctx, ctx, work128, n_work, uint32_t(n_items), H, e_ext);
+    attn_kernel(feat)<<<grid, (feat & kFeatRegs) ? 256u : kThreads, kSmemDynamic, st>>>(tm_q, tm_kv, tm_ctx, ctx, work128, n_work, uint32_t(n_items), H, e_ext);
     P5_CUDA(cudaGetLastError());
 }
 
