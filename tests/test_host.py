@@ -5,6 +5,7 @@ import ctypes as C
 import hashlib
 import json
 import os
+import shutil
 import subprocess
 
 import pytest
@@ -141,6 +142,30 @@ def test_cli_argument_and_contract_errors(tmp_path, tiny_dir):
     assert p.returncode == 1 and "Input is not a directory or a file" in p.stderr
     assert _run([UNICORE, "version"]).returncode == 0
     assert _run([UNICORE, "cluster", "a", "b", "c"]).returncode == 0x30
+
+
+def test_policy_switches_are_accepted_up_to_the_device(tmp_path, tiny_dir):
+    """The three defaults a real Foldseek would have to settle (split length, </s> in the CNN head's input, rare residues)
+    are explicit switches of both host tools: here, without a GPU, they must parse and the run must get as
+    far as the device (exit 1 with the library's no-device message, not a usage error), and the comparison script must
+    refuse to run without a real foldseek."""
+    inp = _make_inputs(tmp_path / "in")
+    p = _run([UNICORE, "createdb", str(inp), str(tmp_path / "o" / "db"), tiny_dir, "--split-len", "0", "--head-eos", "0",
+              "--rare-residues", "own"])
+    assert p.returncode not in (0x40,) and "unknown" not in p.stderr.lower()
+    fa = tmp_path / "x.fasta"
+    fa.write_text(">a\nMKT\n")
+    p = _run([SHIM, "createdb", str(fa), str(tmp_path / "s" / "db"), "--prostt5-model", tiny_dir, "--threads", "2",
+              "--prostt5-split-length", "0", "--prostt5-head-eos", "0", "--prostt5-rare-residues", "own"])
+    assert "unknown option" not in p.stderr
+    p = _run([SHIM, "createdb", str(fa), str(tmp_path / "s" / "db"), "--prostt5-model", tiny_dir, "--no-such-flag", "1"])
+    assert p.returncode == 1 and "unknown option" in p.stderr
+    help_text = _run([UNICORE, "createdb", "--help"])
+    assert "--head-eos" in (help_text.stdout + help_text.stderr) and "--split-len" in (help_text.stdout + help_text.stderr)
+    script = os.path.join(ROOT, "tools", "compare_with_foldseek.sh")
+    if shutil.which("foldseek") is None:
+        p = _run(["bash", script, str(fa), tiny_dir])
+        assert p.returncode == 2 and "foldseek not on PATH" in p.stderr
 
 
 def test_shim_contract(tmp_path):
